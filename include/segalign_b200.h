@@ -1,0 +1,148 @@
+/*
+ * segalign_b200.h -- C ABI of the B200-native seed-filter-extend backend.
+ *
+ * One entry point per function of SegAlign's GPU backend boundary.  Each declaration cites the
+ * reference interface it replaces (paths relative to the gsneha26/SegAlign checkout).  The
+ * signatures use plain pointers and sizes only; the C++ shim that re-exports the reference's
+ * own symbols (g_InitializeInterface ... g_SeedAndFilter, GenerateSeedPosTable) on top of this
+ * ABI is segalign_b200/csrc/shim.cpp, see INTEGRATION.md.
+ *
+ * Error convention (reference: common/cuda_utils.h:4-37, seed_filter_interface.cu:54-69):
+ * the reference prints to stderr and exit()s.  Here every function returns 0 on success or a
+ * negative SA_ERR_* code and records a message retrievable with sa_last_error(); the shim
+ * turns these back into the reference's "print + exit(code)" behaviour.
+ *
+ * Threading: sa_seed_and_filter* may be called concurrently from many host
+ * threads; every other function is called from one control thread, and ref-level calls only
+ * while no seed_and_filter call is in flight.  sa_send_query / sa_clear_query on one buffer
+ * slot are safe while calls run on the other slot.
+ */
+#ifndef SEGALIGN_B200_H
+#define SEGALIGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* HSP / hit record -- src/graph.h:25-30 (segmentPair), 16 bytes */
+typedef struct sa_segment {
+    uint32_t ref_start;   /* block-relative, 0-based */
+    uint32_t query_start; /* block-relative, 0-based (rev-comp coordinates when rev) */
+    uint32_t len;         /* number of bases - 1 */
+    int32_t score;
+} sa_segment;
+
+#define SA_BUFFER_DEPTH 2 /* src/graph.h:14 */
+
+/* exit codes of the reference (scripts/run_segalign:3-13), negated */
+#define SA_OK 0
+#define SA_ERR_NO_GPU (-1)        /* exit(1)  seed_filter_interface.cu:54-57 */
+#define SA_ERR_TOO_MANY_GPUS (-10) /* exit(10) seed_filter_interface.cu:66-69 */
+#define SA_ERR_SET_DEVICE (-11)    /* exit(11) cuda_utils.h:4-10 */
+#define SA_ERR_MALLOC (-12)        /* exit(12) cuda_utils.h:13-19 */
+#define SA_ERR_MEMCPY (-13)        /* exit(13) cuda_utils.h:22-28 */
+#define SA_ERR_FREE (-14)          /* exit(14) cuda_utils.h:31-37 */
+#define SA_ERR_MAX_SEEDS (-20)     /* assert(num_seeds <= MAX_SEEDS) seed_filter.cu:688-692 */
+#define SA_ERR_STATE (-21)         /* call order violated (no ref / table / query loaded) */
+#define SA_ERR_ARG (-22)
+#define SA_ERR_KERNEL (-23)        /* a launch or a stream sync failed */
+
+const char *sa_last_error(void);
+
+/* InitializeInterface -- common/seed_filter_interface.cu:49-80.
+ * num_gpu == -1 uses every visible device.  Returns the device count (>0) or SA_ERR_*.
+ * first_device lets a one-process-per-GPU launcher (torchrun) bind rank r to device r; the
+ * reference always starts at device 0. */
+int sa_initialize_interface(int num_gpu);
+int sa_initialize_interface_at(int first_device, int num_gpu);
+
+/* InitializeProcessor -- src/seed_filter.cu:830-897.  sub_mat is the 8x8 matrix, row = ref
+ * code.  MAX_SEEDS = (transition ? 13 : 1) * wga_chunk; MAX_HITS = 4194304 * GiB(device 0). */
+int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_size,
+                            const int *sub_mat, int xdrop, int hspthresh, int noentropy);
+
+/* Test/oracle knob: the reference's MAX_HITS is a non-static global (seed_filter.cu:21) that a
+ * harness can lower to force the multi-iteration path; 0 restores the device-derived value. */
+int sa_set_max_hits(uint32_t max_hits);
+uint32_t sa_get_max_hits(void);
+
+/* GenerateShapePos -- common/ntcoding.cpp:21-37.  pattern uses 'T'/'1' for care positions
+ * ("TTT0T00TT00T0T0TTTT" for 12of19).  Returns the weight.  The reference keeps this state in
+ * ntcoding.cpp's globals; the shim forwards it. */
+int sa_set_seed_shape(const char *pattern);
+
+/* SendRefWriteRequest -- common/seed_filter_interface.cu:82-101.  Uploads seq[start,start+len)
+ * (ASCII) to every GPU and encodes it. */
+int sa_send_ref(const char *seq, size_t start_addr, uint32_t len);
+
+/* GenerateSeedPosTable -- common/seed_pos_table.cu:49-109.  The table is built ON THE GPU
+ * from the encoded reference block already resident there (sa_send_ref must precede it, as in
+ * src/main.cpp:615-621); ref_str/start_addr are accepted for signature parity and only used
+ * to validate the call.  shape_size = seed span, kmer_size = weight. */
+int sa_generate_seed_pos_table(const char *ref_str, size_t start_addr, uint32_t ref_length,
+                               uint32_t step, int shape_size, int kmer_size);
+
+/* ClearRef -- common/seed_filter_interface.cu:103-113 (frees ref + table on every GPU) */
+int sa_clear_ref(void);
+
+/* SendQueryWriteRequest -- src/seed_filter.cu:899-919.  The reference reads the global
+ * query_DRAM->buffer + start_addr; here the base pointer is explicit. */
+int sa_send_query(const char *query_base, size_t start_addr, uint32_t len, uint32_t buffer);
+
+/* ClearQuery -- src/seed_filter.cu:921-930 */
+int sa_clear_query(uint32_t buffer);
+
+/* SeedAndFilter -- src/seed_filter.cu:682-828.
+ * seeds[i] = (kmer << 32) + query_pos.  On return *out points to a library-owned array of
+ * *out_count records whose element 0 is the header {0, 0, len = total_anchors,
+ * score = num_hits}; release it with sa_release_result().  Returns 0 or SA_ERR_*. */
+int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint32_t buffer,
+                       sa_segment **out, uint32_t *out_count);
+void sa_release_result(sa_segment *out);
+
+/* Device-side seeding: generates the seed words of src/seeder.cpp:57-74 for
+ * query positions [q_start, q_end) of the resident (fwd or rev-comp) query block on the GPU,
+ * then runs the same pipeline as sa_seed_and_filter.  *out_num_seeds (optional) receives the
+ * number of seed words.  A range without any valid seed returns a header-only result with
+ * *out_num_seeds = 0 (the reference's seeder skips the call, seeder.cpp:76). */
+int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev,
+                             uint32_t buffer, sa_segment **out, uint32_t *out_count,
+                             uint32_t *out_num_seeds);
+
+/* ShutdownProcessor -- src/seed_filter.cu:932-940 */
+int sa_shutdown_processor(void);
+
+/* ------------------------------------------------------------------ introspection (tests, bench) */
+
+/* Copies the device seed position table of GPU 0 back to the host.  index_out holds 4^weight
+ * inclusive end offsets (what the reference uploads as index_table+1); pos_out holds num_pos
+ * positions.  Pass NULL to query sizes only. */
+int sa_debug_get_table(uint32_t *index_size, uint32_t *num_pos, uint32_t *index_out,
+                       uint32_t *pos_out);
+/* Copies the encoded (1 byte/base) ref block (which=0), query fwd (1) or query rc (2) of slot
+ * `buffer` from GPU 0. */
+int sa_debug_get_encoded(int which, uint32_t buffer, uint8_t *out, uint32_t len);
+
+/* Per-phase device timings (CUDA events on the launching stream) and counters accumulated
+ * since the last reset, summed over all GPUs of this process. */
+typedef struct sa_stats {
+    uint64_t calls, seeds, hits, survivors, anchors_pre_dedupe, hsps;
+    uint64_t ext_cells;        /* ref bases scanned by the exact extension beyond 32/side */
+    double ms_h2d, ms_count_scan, ms_lookup, ms_prefilter, ms_extend, ms_sort, ms_d2h;
+    double ms_ref_encode, ms_table_build, ms_query_encode;
+    uint64_t launches;         /* kernels launched by this library */
+} sa_stats;
+int sa_get_stats(sa_stats *out);
+int sa_reset_stats(void);
+/* 1 = record per-phase CUDA events (adds stream syncs; off by default) */
+int sa_set_profiling(int enabled);
+
+const char *sa_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

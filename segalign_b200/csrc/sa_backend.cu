@@ -1,0 +1,773 @@
+// sa_backend.cu -- host side of the B200 backend + the C ABI of include/segalign_b200.h.
+//
+// Mirrors the reference backend's host logic (common/seed_filter_interface.cu:49-113,
+// common/seed_pos_table.cu:33-109, src/seed_filter.cu:682-940) with a different execution
+// model: per-GPU contexts, several independent workspaces (stream + buffers) per GPU so that
+// concurrent SeedAndFilter calls from the host pipeline overlap, table build on the device,
+// and buffers that grow on demand instead of a 36-byte-per-MAX_HITS up-front allocation.
+// There is NO CPU fallback: every entry point fails with an SA_ERR_* code if CUDA fails.
+#include <algorithm>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "kernels_encode.cuh"
+#include "kernels_extend.cuh"
+#include "kernels_lookup.cuh"
+#include "kernels_sort.cuh"
+#include "sa_common.cuh"
+
+using namespace sa;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr, code)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail((code), "%s failed with error \" %s \" (%s:%d)", #expr,             \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                        \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != SA_OK) return _r; \
+    } while (0)
+
+constexpr int kSmCount = 148;
+inline int grid_for(size_t n, int block, int per_sm = 8) {
+    size_t want = (n + block - 1) / block;
+    size_t cap = (size_t)kSmCount * per_sm;
+    return (int)std::max<size_t>(1, std::min(want, cap));
+}
+
+template <typename T>
+int ensure(T *&ptr, size_t &cap, size_t need, const char *tag, size_t slack_num = 5,
+           size_t slack_den = 4) {
+    if (need <= cap && ptr) return SA_OK;
+    if (ptr) CU(cudaFree(ptr), SA_ERR_FREE);
+    ptr = nullptr;
+    size_t n = std::max<size_t>(need * slack_num / slack_den, 1024);
+    cudaError_t e = cudaMalloc((void **)&ptr, n * sizeof(T));
+    if (e != cudaSuccess) {
+        cap = 0;
+        return fail(SA_ERR_MALLOC, "cudaMalloc of %zu bytes for %s failed with error \" %s \"",
+                    n * sizeof(T), tag, cudaGetErrorString(e));
+    }
+    cap = n;
+    return SA_OK;
+}
+
+struct Workspace {
+    int gpu = 0; // index into G.gpus
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[10] = {};
+    uint64_t *d_seeds = nullptr; size_t seeds_cap = 0;
+    uint32_t *d_prefix = nullptr; size_t prefix_cap = 0;
+    uint32_t *d_limit_pos = nullptr; size_t limit_cap = 0;
+    uint32_t *d_hit_bound = nullptr; size_t bound_cap = 0;
+    uint32_t *d_plan = nullptr;      // [0]=num_iter [1]=num_hits
+    uint32_t *d_counters = nullptr;  // [0]=anchor cursor [1]=dedupe cursor [2..3]=ext cells
+    uint2 *d_hits = nullptr; size_t hits_cap = 0;
+    Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
+    Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
+    sa_segment *d_out = nullptr; size_t out_cap = 0;
+    uint8_t *d_temp = nullptr; size_t temp_cap = 0;
+    uint32_t *d_flags = nullptr; size_t flags_cap = 0;
+    uint32_t *d_excl = nullptr; size_t excl_cap = 0;
+    uint32_t *h_small = nullptr; // pinned, 16 words
+};
+
+struct GpuCtx {
+    int device = 0;
+    cudaStream_t ctrl = nullptr;
+    SeqPlanes ref;
+    SeqPlanes q_fwd[SA_BUFFER_DEPTH], q_rc[SA_BUFFER_DEPTH];
+    uint32_t *d_index = nullptr;
+    uint32_t *d_pos = nullptr;
+    uint32_t index_size = 0, num_pos = 0;
+    int *d_sub_mat = nullptr;
+    std::vector<Workspace *> ws;
+};
+
+struct Global {
+    bool interface_ready = false, processor_ready = false;
+    std::vector<GpuCtx> gpus;
+    // InitializeProcessor scalars (seed_filter.cu:20-27)
+    uint32_t max_seeds = 0, max_hits = 0, max_hits_device = 0, seed_size = 0;
+    int sub_mat[64] = {};
+    int xdrop = 0, hspthresh = 0, noentropy = 0, diag_all_positive = 0, transition = 0;
+    uint32_t ref_len = 0;
+    bool ref_loaded = false, table_ready = false;
+    uint32_t query_len[SA_BUFFER_DEPTH] = {};
+    bool query_loaded[SA_BUFFER_DEPTH] = {};
+    ShapeDesc shape = {};
+    bool shape_set = false;
+    // workspace pool (the reference's mu/cv/available_gpus, store_gpu.h:4-6)
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<Workspace *> free_ws;
+    int ws_per_gpu = 3;
+    // stats
+    std::mutex stats_mu;
+    sa_stats stats = {};
+    bool profiling = false;
+};
+
+Global G;
+
+void add_launches(uint64_t n) {
+    std::lock_guard<std::mutex> l(G.stats_mu);
+    G.stats.launches += n;
+}
+
+// ------------------------------------------------------------------ sequence planes
+int free_planes(SeqPlanes &p) {
+    if (p.b8) CU(cudaFree(p.b8), SA_ERR_FREE);
+    if (p.p2) CU(cudaFree(p.p2), SA_ERR_FREE);
+    if (p.m1) CU(cudaFree(p.m1), SA_ERR_FREE);
+    p = SeqPlanes();
+    return SA_OK;
+}
+
+int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag) {
+    p.len = len;
+    p.words = ((size_t)len + 31) / 32 + PAD_WORDS;
+    cudaError_t e = cudaMalloc((void **)&p.b8, (size_t)len + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.p2, p.words * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.m1, p.words * sizeof(uint32_t));
+    if (e != cudaSuccess)
+        return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for %s failed with error \" %s \"",
+                    (unsigned long)len, tag, cudaGetErrorString(e));
+    return SA_OK;
+}
+
+// upload ASCII and encode; fwd always, rc if rc != nullptr
+int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, SeqPlanes *rc,
+                      const char *tag) {
+    uint8_t *d_tmp = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_tmp, (size_t)len + 64);
+    if (e != cudaSuccess)
+        return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for tmp_%s failed with error \" %s \"",
+                    (unsigned long)len, tag, cudaGetErrorString(e));
+    e = cudaMemcpyAsync(d_tmp, src, len, cudaMemcpyHostToDevice, g.ctrl);
+    if (e != cudaSuccess) {
+        cudaFree(d_tmp);
+        return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for %s failed with error \" %s \"",
+                    (unsigned long)len, tag, cudaGetErrorString(e));
+    }
+    TRY(alloc_planes(fwd, len, tag));
+    if (rc) TRY(alloc_planes(*rc, len, tag));
+    if (len > 0) {
+        int grid = grid_for(((size_t)len + 15) / 16, 256);
+        k_encode_b8<<<grid, 256, 0, g.ctrl>>>(d_tmp, len, fwd.b8, rc ? rc->b8 : nullptr);
+    }
+    k_pack_planes<<<grid_for(fwd.words, 256), 256, 0, g.ctrl>>>(fwd.b8, len, fwd.p2, fwd.m1,
+                                                                 (uint32_t)fwd.words);
+    if (rc)
+        k_pack_planes<<<grid_for(rc->words, 256), 256, 0, g.ctrl>>>(rc->b8, len, rc->p2, rc->m1,
+                                                                     (uint32_t)rc->words);
+    add_launches(rc ? 3 : 2);
+    CU(cudaGetLastError(), SA_ERR_KERNEL);
+    CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+    CU(cudaFree(d_tmp), SA_ERR_FREE);
+    return SA_OK;
+}
+
+// ------------------------------------------------------------------ workspace pool
+Workspace *acquire_ws() {
+    std::unique_lock<std::mutex> lk(G.mu);
+    G.cv.wait(lk, [] { return !G.free_ws.empty(); });
+    Workspace *w = G.free_ws.back();
+    G.free_ws.pop_back();
+    return w;
+}
+void release_ws(Workspace *w) {
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        G.free_ws.push_back(w);
+    }
+    G.cv.notify_one();
+}
+struct WsGuard {
+    Workspace *w;
+    explicit WsGuard(Workspace *w_) : w(w_) {}
+    ~WsGuard() { release_ws(w); }
+};
+
+int make_workspace(int gpu_index, Workspace *&out) {
+    Workspace *w = new Workspace();
+    w->gpu = gpu_index;
+    CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking), SA_ERR_KERNEL);
+    for (auto &e : w->ev) CU(cudaEventCreate(&e), SA_ERR_KERNEL);
+    CU(cudaMalloc((void **)&w->d_plan, 4 * sizeof(uint32_t)), SA_ERR_MALLOC);
+    CU(cudaMalloc((void **)&w->d_counters, 8 * sizeof(uint32_t)), SA_ERR_MALLOC);
+    CU(cudaMallocHost((void **)&w->h_small, 16 * sizeof(uint32_t)), SA_ERR_MALLOC);
+    TRY(ensure(w->d_seeds, w->seeds_cap, std::max<size_t>(G.max_seeds, 1024), "seed_offsets", 1, 1));
+    TRY(ensure(w->d_prefix, w->prefix_cap, std::max<size_t>(G.max_seeds, 1024), "hit_num", 1, 1));
+    TRY(ensure(w->d_limit_pos, w->limit_cap, 64, "limit_pos", 1, 1));
+    TRY(ensure(w->d_hit_bound, w->bound_cap, 64, "hit_bound", 1, 1));
+    out = w;
+    return SA_OK;
+}
+
+void destroy_workspace(Workspace *w) {
+    cudaFree(w->d_seeds); cudaFree(w->d_prefix); cudaFree(w->d_limit_pos);
+    cudaFree(w->d_hit_bound); cudaFree(w->d_plan); cudaFree(w->d_counters);
+    cudaFree(w->d_hits); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
+    cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
+    cudaFreeHost(w->h_small);
+    for (auto &e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+// ------------------------------------------------------------------ the per-call pipeline
+struct PhaseTimer {
+    Workspace *w;
+    bool on;
+    int n = 0;
+    explicit PhaseTimer(Workspace *w_) : w(w_), on(G.profiling) {}
+    void mark() { if (on && n < 10) cudaEventRecord(w->ev[n++], w->stream); }
+    float ms(int a, int b) const {
+        float t = 0;
+        if (on && b < n) cudaEventElapsedTime(&t, w->ev[a], w->ev[b]);
+        return t;
+    }
+};
+
+int sort_anchors(Workspace *w, Anchor *keys, uint32_t n, bool lastz) {
+    size_t bytes = 0;
+    if (lastz) CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, CompLastz(), w->stream), SA_ERR_KERNEL);
+    else CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, CompDiag(), w->stream), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "sort_temp"));
+    if (lastz) CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, CompLastz(), w->stream), SA_ERR_KERNEL);
+    else CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, CompDiag(), w->stream), SA_ERR_KERNEL);
+    return SA_OK;
+}
+
+// Seeds are already in w->d_seeds.  Produces the malloc'd result (header + HSPs).
+int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_segment **out,
+                 uint32_t *out_count, PhaseTimer &pt) {
+    GpuCtx &g = G.gpus[w->gpu];
+    cudaStream_t st = w->stream;
+    uint64_t launches = 0;
+    uint32_t num_hits = 0, num_iter = 0, n_pre = 0, n_final = 0;
+    unsigned long long ext_cells = 0;
+
+    // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
+    k_count_hits<<<grid_for(num_seeds, 256), 256, 0, st>>>(w->d_seeds, num_seeds, g.d_index, w->d_prefix);
+    size_t bytes = 0;
+    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)num_seeds, st), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
+    CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)num_seeds, st), SA_ERR_KERNEL);
+    launches += 3;
+    // 2. iteration plan on the device (seed_filter.cu:718-745)
+    for (;;) {
+        k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, num_seeds, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
+                                            w->d_limit_pos, w->d_hit_bound, w->d_plan);
+        launches++;
+        CU(cudaMemcpyAsync(w->h_small, w->d_plan, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+        num_iter = w->h_small[0];
+        num_hits = w->h_small[1];
+        if (num_iter != 0xFFFFFFFFu) break;
+        size_t need = (size_t)num_hits / G.max_hits + 2;
+        TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
+        TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
+    }
+    pt.mark(); // [2] after count/scan/plan
+
+    if (num_hits > 0) {
+        // 3. flat hit expansion (seed_filter.cu:760)
+        TRY(ensure(w->d_hits, w->hits_cap, num_hits, "hsp"));
+        k_expand_hits<<<grid_for(((size_t)num_seeds + 31) / 32 * 32, 256), 256, 0, st>>>(
+            w->d_seeds, num_seeds, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits);
+        launches++;
+        pt.mark(); // [3] after lookup
+        // 4. extension + append (seed_filter.cu:762-774)
+        ExtendParams P;
+        const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
+        P.rb8 = g.ref.b8; P.rp2 = g.ref.p2; P.rm1 = g.ref.m1; P.ref_len = g.ref.len;
+        P.qb8 = q.b8; P.qp2 = q.p2; P.qm1 = q.m1; P.query_len = q.len;
+        P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
+        P.diag_all_positive = G.diag_all_positive;
+        if (!w->d_anchors_a) TRY(ensure(w->d_anchors_a, w->anchors_a_cap, (size_t)1 << 20, "hsp_reduced", 1, 1));
+        for (;;) {
+            CU(cudaMemsetAsync(w->d_counters, 0, 8 * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+            k_extend_hits<<<grid_for(num_hits, 128, 16), 128, 0, st>>>(
+                P, g.d_sub_mat, w->d_hits, 0u, num_hits, w->d_hit_bound, w->d_plan, w->d_anchors_a,
+                (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu), w->d_counters);
+            launches++;
+            CU(cudaMemcpyAsync(w->h_small, w->d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+            CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+            n_pre = w->h_small[0];
+            memcpy(&ext_cells, &w->h_small[2], 8);
+            if (n_pre <= w->anchors_a_cap) break;
+            TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced")); // rare: rerun
+        }
+        pt.mark(); // [4] after extension
+        // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782)
+        if (n_pre > 0) {
+            TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
+            TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
+            k_dedupe<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + 1);
+            CU(cudaMemcpyAsync(w->h_small, w->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+            CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+            n_final = w->h_small[0];
+            TRY(sort_anchors(w, w->d_anchors_b, n_final, true));
+            TRY(ensure(w->d_out, w->out_cap, n_final, "hsp_out"));
+            k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_b, n_final, w->d_out);
+            launches += 8;
+        }
+        pt.mark(); // [5] after sort
+    }
+    // 6. result (seed_filter.cu:786-788, :804-822)
+    sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
+    if (!res) return fail(SA_ERR_MALLOC, "malloc of result failed");
+    res[0].ref_start = 0;
+    res[0].query_start = 0;
+    res[0].len = n_final;
+    res[0].score = (int32_t)num_hits;
+    if (n_final > 0) {
+        cudaError_t e = cudaMemcpyAsync(res + 1, w->d_out, (size_t)n_final * sizeof(sa_segment), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            free(res);
+            return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for hsp_output failed with error \" %s \"",
+                        (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
+        }
+    }
+    pt.mark(); // [6] after D2H
+    if (pt.on) CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+    CU(cudaGetLastError(), SA_ERR_KERNEL);
+    *out = res;
+    *out_count = n_final + 1;
+    {
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        sa_stats &s = G.stats;
+        s.calls++; s.seeds += num_seeds; s.hits += num_hits; s.survivors += num_hits;
+        s.anchors_pre_dedupe += n_pre; s.hsps += n_final; s.ext_cells += ext_cells;
+        s.launches += launches;
+        if (pt.on) {
+            // marks: 0 start, 1 after H2D/seed gen, 2 plan, [3 lookup, 4 extend, 5 sort], last d2h
+            s.ms_h2d += pt.ms(0, 1);
+            s.ms_count_scan += pt.ms(1, 2);
+            if (num_hits > 0) {
+                s.ms_lookup += pt.ms(2, 3);
+                s.ms_extend += pt.ms(3, 4);
+                s.ms_sort += pt.ms(4, 5);
+                s.ms_d2h += pt.ms(5, 6);
+            } else {
+                s.ms_d2h += pt.ms(2, 3);
+            }
+        }
+    }
+    return SA_OK;
+}
+
+int check_call_state(uint32_t buffer) {
+    if (!G.processor_ready) return fail(SA_ERR_STATE, "InitializeProcessor has not been called");
+    if (!G.ref_loaded || !G.table_ready) return fail(SA_ERR_STATE, "no reference block / seed position table on the GPU");
+    if (buffer >= SA_BUFFER_DEPTH || !G.query_loaded[buffer]) return fail(SA_ERR_STATE, "no query block in buffer %u", buffer);
+    return SA_OK;
+}
+
+} // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *sa_last_error(void) { return g_err.c_str(); }
+const char *sa_version(void) { return "segalign_b200 0.1 (sm_100a)"; }
+
+int sa_initialize_interface_at(int first_device, int num_gpu) {
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess || n <= 0) return fail(SA_ERR_NO_GPU, "Error: No GPU device found!");
+    if (first_device < 0 || first_device >= n) return fail(SA_ERR_ARG, "first_device %d out of range", first_device);
+    int avail = n - first_device;
+    int use = num_gpu == -1 ? avail : num_gpu;
+    if (use > avail || use <= 0) return fail(SA_ERR_TOO_MANY_GPUS, "Requested GPUs greater than available GPUs");
+    G.gpus.clear();
+    G.gpus.resize(use);
+    for (int i = 0; i < use; i++) {
+        G.gpus[i].device = first_device + i;
+        CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
+        CU(cudaStreamCreateWithFlags(&G.gpus[i].ctrl, cudaStreamNonBlocking), SA_ERR_KERNEL);
+    }
+    fprintf(stderr, "Using %d GPU(s)\n", use);
+    G.interface_ready = true;
+    return use;
+}
+
+int sa_initialize_interface(int num_gpu) { return sa_initialize_interface_at(0, num_gpu); }
+
+int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_size,
+                            const int *sub_mat, int xdrop, int hspthresh, int noentropy) {
+    if (!G.interface_ready) return fail(SA_ERR_STATE, "InitializeInterface has not been called");
+    if (!sub_mat) return fail(SA_ERR_ARG, "sub_mat is NULL");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, G.gpus[0].device), SA_ERR_SET_DEVICE);
+    // seed_filter.cu:834-841, same float arithmetic
+    float global_mem_gb = static_cast<float>(prop.totalGlobalMem / 1073741824.0f);
+    G.max_seeds = transition ? 13u * wga_chunk : wga_chunk;
+    G.max_hits_device = (uint32_t)(int)(4194304 * global_mem_gb);
+    G.max_hits = G.max_hits_device;
+    G.transition = transition;
+    G.seed_size = seed_size;
+    G.xdrop = xdrop;
+    G.hspthresh = hspthresh;
+    G.noentropy = noentropy;
+    memcpy(G.sub_mat, sub_mat, sizeof(G.sub_mat));
+    G.diag_all_positive = sub_mat[0] > 0 && sub_mat[9] > 0 && sub_mat[18] > 0 && sub_mat[27] > 0;
+    const char *env = getenv("SEGALIGN_B200_STREAMS");
+    if (env && atoi(env) > 0) G.ws_per_gpu = atoi(env);
+    for (size_t i = 0; i < G.gpus.size(); i++) {
+        GpuCtx &g = G.gpus[i];
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        CU(cudaMalloc((void **)&g.d_sub_mat, 64 * sizeof(int)), SA_ERR_MALLOC);
+        CU(cudaMemcpy(g.d_sub_mat, sub_mat, 64 * sizeof(int), cudaMemcpyHostToDevice), SA_ERR_MEMCPY);
+        for (int k = 0; k < G.ws_per_gpu; k++) {
+            Workspace *w = nullptr;
+            TRY(make_workspace((int)i, w));
+            g.ws.push_back(w);
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        G.free_ws.clear();
+        // interleave so consecutive calls spread over the GPUs first
+        for (int k = 0; k < G.ws_per_gpu; k++)
+            for (size_t i = 0; i < G.gpus.size(); i++) G.free_ws.push_back(G.gpus[i].ws[k]);
+        std::reverse(G.free_ws.begin(), G.free_ws.end());
+    }
+    G.processor_ready = true;
+    return SA_OK;
+}
+
+int sa_set_max_hits(uint32_t max_hits) {
+    G.max_hits = max_hits ? max_hits : G.max_hits_device;
+    return SA_OK;
+}
+uint32_t sa_get_max_hits(void) { return G.max_hits; }
+
+int sa_set_seed_shape(const char *pattern) {
+    if (!pattern) return fail(SA_ERR_ARG, "pattern is NULL");
+    size_t n = strlen(pattern);
+    if (n == 0 || n > 32) return fail(SA_ERR_ARG, "seed span must be 1..32");
+    ShapeDesc sh = {};
+    sh.span = (int)n;
+    for (size_t i = 0; i < n; i++) { // ntcoding.cpp:21-37
+        if (pattern[i] == '1' || pattern[i] == 'T') {
+            sh.pos[sh.weight] = (uint8_t)i;
+            sh.trans[sh.weight] = pattern[i] == 'T';
+            sh.num_trans += pattern[i] == 'T';
+            sh.weight++;
+        }
+    }
+    if (sh.weight <= 3 || sh.weight > 15) return fail(SA_ERR_ARG, "seed weight must be 4..15"); // seed_pos_table.cu:51-52
+    G.shape = sh;
+    G.shape_set = true;
+    return sh.weight;
+}
+
+int sa_send_ref(const char *seq, size_t start_addr, uint32_t len) {
+    if (!G.interface_ready) return fail(SA_ERR_STATE, "InitializeInterface has not been called");
+    if (G.ref_loaded) return fail(SA_ERR_STATE, "ClearRef must precede a second SendRefWriteRequest");
+    G.ref_len = len;
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, g.ctrl);
+        TRY(upload_and_encode(g, seq + start_addr, len, g.ref, nullptr, "ref_seq"));
+        cudaEventRecord(e1, g.ctrl);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        G.stats.ms_ref_encode += ms;
+    }
+    G.ref_loaded = true;
+    return SA_OK;
+}
+
+int sa_generate_seed_pos_table(const char *ref_str, size_t start_addr, uint32_t ref_length,
+                               uint32_t step, int shape_size, int kmer_size) {
+    (void)ref_str; (void)start_addr;
+    if (!G.ref_loaded) return fail(SA_ERR_STATE, "SendRefWriteRequest must precede GenerateSeedPosTable");
+    if (!G.shape_set) return fail(SA_ERR_STATE, "seed shape not set (GenerateShapePos)");
+    if (ref_length != G.ref_len) return fail(SA_ERR_ARG, "ref_length %u differs from the resident block (%u)", ref_length, G.ref_len);
+    if (shape_size != G.shape.span || kmer_size != G.shape.weight) return fail(SA_ERR_ARG, "shape_size/kmer_size do not match the seed shape");
+    if (step == 0) return fail(SA_ERR_ARG, "step must be > 0");
+    if (G.table_ready) return fail(SA_ERR_STATE, "ClearRef must precede a second GenerateSeedPosTable");
+    // seed_pos_table.cu:58-64
+    uint32_t offset = ((uint32_t)shape_size + 1) % step;
+    uint32_t start_offset = step - offset;
+    uint32_t num_steps = ref_length >= (uint32_t)shape_size ? (ref_length - shape_size + offset) / step : 0;
+    uint32_t index_size = 1u << (2 * kmer_size);
+    int end_bit = 2 * kmer_size + 1;
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        cudaStream_t st = g.ctrl;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
+        size_t n = std::max<uint32_t>(num_steps, 1);
+        CU(cudaMalloc((void **)&g.d_index, (size_t)index_size * sizeof(uint32_t)), SA_ERR_MALLOC);
+        CU(cudaMemsetAsync(g.d_index, 0, (size_t)index_size * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        CU(cudaMalloc((void **)&keys_a, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&keys_b, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&vals_a, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&vals_b, n * 4), SA_ERR_MALLOC);
+        uint64_t launches = 0;
+        if (num_steps > 0) {
+            k_table_keys<<<grid_for(num_steps, 256), 256, 0, st>>>(g.ref.p2, g.ref.m1, G.shape, start_offset, step,
+                                                                   num_steps, keys_a, vals_a, g.d_index);
+            launches++;
+        }
+        // histogram -> inclusive end offsets (seed_pos_table.cu:83; device sees index_table+1)
+        size_t bytes = 0, bytes2 = 0;
+        CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, g.d_index, g.d_index, (int)index_size, st), SA_ERR_KERNEL);
+        cub::DoubleBuffer<uint32_t> dk(keys_a, keys_b), dv(vals_a, vals_b);
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes2, dk, dv, (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
+        void *d_temp = nullptr;
+        CU(cudaMalloc(&d_temp, std::max(bytes, bytes2) + 256), SA_ERR_MALLOC);
+        CU(cub::DeviceScan::InclusiveSum(d_temp, bytes, g.d_index, g.d_index, (int)index_size, st), SA_ERR_KERNEL);
+        launches += 2;
+        uint32_t num_pos = 0;
+        CU(cudaMemcpyAsync(&num_pos, g.d_index + index_size - 1, 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        if (num_steps > 0) {
+            CU(cub::DeviceRadixSort::SortPairs(d_temp, bytes2, dk, dv, (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
+            launches += 2 * ((end_bit + 7) / 8) + 1;
+        }
+        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+        CU(cudaMalloc((void **)&g.d_pos, std::max<size_t>(num_pos, 1) * sizeof(uint32_t)), SA_ERR_MALLOC);
+        if (num_pos > 0)
+            CU(cudaMemcpyAsync(g.d_pos, dv.Current(), (size_t)num_pos * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), SA_ERR_MEMCPY);
+        cudaEventRecord(e1, st);
+        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        CU(cudaFree(keys_a), SA_ERR_FREE); CU(cudaFree(keys_b), SA_ERR_FREE);
+        CU(cudaFree(vals_a), SA_ERR_FREE); CU(cudaFree(vals_b), SA_ERR_FREE);
+        CU(cudaFree(d_temp), SA_ERR_FREE);
+        g.index_size = index_size;
+        g.num_pos = num_pos;
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        G.stats.ms_table_build += ms;
+        G.stats.launches += launches;
+    }
+    G.table_ready = true;
+    return SA_OK;
+}
+
+int sa_clear_ref(void) {
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        TRY(free_planes(g.ref));
+        if (g.d_index) CU(cudaFree(g.d_index), SA_ERR_FREE);
+        if (g.d_pos) CU(cudaFree(g.d_pos), SA_ERR_FREE);
+        g.d_index = g.d_pos = nullptr;
+        g.index_size = g.num_pos = 0;
+    }
+    G.ref_loaded = G.table_ready = false;
+    return SA_OK;
+}
+
+int sa_send_query(const char *query_base, size_t start_addr, uint32_t len, uint32_t buffer) {
+    if (!G.interface_ready) return fail(SA_ERR_STATE, "InitializeInterface has not been called");
+    if (buffer >= SA_BUFFER_DEPTH) return fail(SA_ERR_ARG, "buffer %u out of range", buffer);
+    if (G.query_loaded[buffer]) return fail(SA_ERR_STATE, "ClearQuery(%u) must precede a refill", buffer);
+    G.query_len[buffer] = len;
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, g.ctrl);
+        TRY(upload_and_encode(g, query_base + start_addr, len, g.q_fwd[buffer], &g.q_rc[buffer], "query_seq"));
+        cudaEventRecord(e1, g.ctrl);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        G.stats.ms_query_encode += ms;
+    }
+    G.query_loaded[buffer] = true;
+    return SA_OK;
+}
+
+int sa_clear_query(uint32_t buffer) {
+    if (buffer >= SA_BUFFER_DEPTH) return fail(SA_ERR_ARG, "buffer %u out of range", buffer);
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        TRY(free_planes(g.q_fwd[buffer]));
+        TRY(free_planes(g.q_rc[buffer]));
+    }
+    G.query_loaded[buffer] = false;
+    return SA_OK;
+}
+
+int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint32_t buffer,
+                       sa_segment **out, uint32_t *out_count) {
+    if (!out || !out_count) return fail(SA_ERR_ARG, "out/out_count is NULL");
+    TRY(check_call_state(buffer));
+    if (num_seeds > G.max_seeds) { // seed_filter.cu:688-692
+        printf("MAX_SEEDS exceeded\n");
+        return fail(SA_ERR_MAX_SEEDS, "num_seeds %u > MAX_SEEDS %u", num_seeds, G.max_seeds);
+    }
+    if (num_seeds == 0) { // the reference's seeder never makes this call (seeder.cpp:76)
+        sa_segment *res = (sa_segment *)calloc(1, sizeof(sa_segment));
+        *out = res; *out_count = 1;
+        return SA_OK;
+    }
+    if (!seeds) return fail(SA_ERR_ARG, "seeds is NULL");
+    Workspace *w = acquire_ws();
+    WsGuard guard(w);
+    CU(cudaSetDevice(G.gpus[w->gpu].device), SA_ERR_SET_DEVICE);
+    PhaseTimer pt(w);
+    pt.mark(); // [0]
+    TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
+    TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
+    CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    pt.mark(); // [1]
+    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
+}
+
+int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev,
+                             uint32_t buffer, sa_segment **out, uint32_t *out_count,
+                             uint32_t *out_num_seeds) {
+    if (!out || !out_count) return fail(SA_ERR_ARG, "out/out_count is NULL");
+    TRY(check_call_state(buffer));
+    if (q_end < q_start) return fail(SA_ERR_ARG, "q_end < q_start");
+    Workspace *w = acquire_ws();
+    WsGuard guard(w);
+    GpuCtx &g = G.gpus[w->gpu];
+    CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+    const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
+    if (q_end > q.len) return fail(SA_ERR_ARG, "range [%u,%u) exceeds the query block (%u)", q_start, q_end, q.len);
+    PhaseTimer pt(w);
+    pt.mark(); // [0]
+    uint32_t n = q_end - q_start, num_seeds = 0;
+    const uint32_t per = 1u + (transition ? (uint32_t)G.shape.num_trans : 0u);
+    if (n > 0) {
+        cudaStream_t st = w->stream;
+        TRY(ensure(w->d_flags, w->flags_cap, n, "seed_flags"));
+        TRY(ensure(w->d_excl, w->excl_cap, (size_t)n + 1, "seed_excl"));
+        k_seed_flags<<<grid_for(n, 256), 256, 0, st>>>(q.m1, G.shape.span, q_start, q_end, w->d_flags);
+        size_t bytes = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+        TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
+        CU(cub::DeviceScan::ExclusiveSum(w->d_temp, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+        CU(cudaMemcpyAsync(w->h_small, w->d_excl + (n - 1), 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(w->h_small + 1, w->d_flags + (n - 1), 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+        uint32_t valid = w->h_small[0] + w->h_small[1];
+        num_seeds = valid * per;
+        add_launches(3);
+        if (num_seeds > G.max_seeds) {
+            printf("MAX_SEEDS exceeded\n");
+            return fail(SA_ERR_MAX_SEEDS, "num_seeds %u > MAX_SEEDS %u", num_seeds, G.max_seeds);
+        }
+        if (num_seeds > 0) {
+            TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
+            TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
+            k_seed_emit<<<grid_for(n, 256), 256, 0, st>>>(q.p2, w->d_flags, w->d_excl, G.shape, transition, q_start, q_end, w->d_seeds);
+            add_launches(1);
+        }
+    }
+    if (out_num_seeds) *out_num_seeds = num_seeds;
+    if (num_seeds == 0) {
+        sa_segment *res = (sa_segment *)calloc(1, sizeof(sa_segment));
+        *out = res; *out_count = 1;
+        return SA_OK;
+    }
+    pt.mark(); // [1]
+    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
+}
+
+void sa_release_result(sa_segment *out) { free(out); }
+
+int sa_shutdown_processor(void) {
+    for (auto &g : G.gpus) {
+        cudaSetDevice(g.device);
+        for (auto *w : g.ws) destroy_workspace(w);
+        g.ws.clear();
+        free_planes(g.ref);
+        for (int b = 0; b < SA_BUFFER_DEPTH; b++) { free_planes(g.q_fwd[b]); free_planes(g.q_rc[b]); }
+        cudaFree(g.d_index); cudaFree(g.d_pos); cudaFree(g.d_sub_mat);
+        g.d_index = g.d_pos = nullptr; g.d_sub_mat = nullptr;
+        if (g.ctrl) cudaStreamDestroy(g.ctrl);
+        g.ctrl = nullptr;
+    }
+    {
+        std::lock_guard<std::mutex> lk(G.mu);
+        G.free_ws.clear();
+    }
+    G.gpus.clear();
+    G.interface_ready = G.processor_ready = G.ref_loaded = G.table_ready = false;
+    for (int b = 0; b < SA_BUFFER_DEPTH; b++) G.query_loaded[b] = false;
+    return SA_OK;
+}
+
+int sa_debug_get_table(uint32_t *index_size, uint32_t *num_pos, uint32_t *index_out, uint32_t *pos_out) {
+    if (!G.table_ready) return fail(SA_ERR_STATE, "no seed position table");
+    GpuCtx &g = G.gpus[0];
+    CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+    if (index_size) *index_size = g.index_size;
+    if (num_pos) *num_pos = g.num_pos;
+    if (index_out) CU(cudaMemcpy(index_out, g.d_index, (size_t)g.index_size * 4, cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
+    if (pos_out && g.num_pos) CU(cudaMemcpy(pos_out, g.d_pos, (size_t)g.num_pos * 4, cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
+    return SA_OK;
+}
+
+int sa_debug_get_encoded(int which, uint32_t buffer, uint8_t *out, uint32_t len) {
+    if (!G.interface_ready || G.gpus.empty()) return fail(SA_ERR_STATE, "not initialised");
+    GpuCtx &g = G.gpus[0];
+    CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+    const SeqPlanes *p = nullptr;
+    if (which == 0) p = &g.ref;
+    else if (buffer < SA_BUFFER_DEPTH) p = which == 1 ? &g.q_fwd[buffer] : &g.q_rc[buffer];
+    if (!p || !p->b8 || len > p->len) return fail(SA_ERR_ARG, "no such encoded block");
+    CU(cudaMemcpy(out, p->b8, len, cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
+    return SA_OK;
+}
+
+int sa_get_stats(sa_stats *out) {
+    if (!out) return fail(SA_ERR_ARG, "out is NULL");
+    std::lock_guard<std::mutex> l(G.stats_mu);
+    *out = G.stats;
+    return SA_OK;
+}
+int sa_reset_stats(void) {
+    std::lock_guard<std::mutex> l(G.stats_mu);
+    G.stats = sa_stats();
+    return SA_OK;
+}
+int sa_set_profiling(int enabled) { G.profiling = enabled != 0; return SA_OK; }
+
+} // extern "C"

@@ -1,0 +1,368 @@
+"""Shared test harness: seeded synthetic cases, the oracle_runner case/dump file formats, and
+the three ways a case is run (new CUDA backend through the C ABI, CPU oracle, reference dump).
+
+A case is the unit the reference's pipeline hands to the backend for one (ref block, query
+block) pair: src/main.cpp:613-661 (uploads + table), src/seeder.cpp:48-120 (per-chunk seed
+vectors, both strands), src/seed_filter.cu:682-828 (SeedAndFilter).
+"""
+from __future__ import annotations
+
+import hashlib
+import struct
+import subprocess
+import sys
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+from segalign_b200 import genome  # noqa: E402
+
+GOLDEN_DIR = ROOT / "tests" / "golden"
+ORACLE_RUNNER = ROOT / "oracle" / "_ref" / "oracle_runner"
+NEW_RUNNER = ROOT / "oracle" / "_ref" / "new_runner"
+
+SEGMENT_DTYPE = np.dtype([("ref_start", "<u4"), ("query_start", "<u4"), ("len", "<u4"), ("score", "<i4")])
+
+
+@dataclass
+class Case:
+    name: str
+    gen: str                      # generator name in GENERATORS
+    gen_args: dict = field(default_factory=dict)
+    rng_seed: int = 20261017
+    seed_shape: str = "12of19"
+    transition: bool = True
+    step: int = 1
+    xdrop: int = 910
+    hspthresh: int = 3000
+    noentropy: bool = False
+    wga_chunk: int = 250_000
+    lastz_interval: int = 10_000_000
+    max_hits_override: int = 0    # >0 forces the multi-iteration path
+    strand: str = "both"
+    ambiguous: str = ""
+
+    def inputs(self):
+        rng = np.random.default_rng(self.rng_seed)
+        ref, query = GENERATORS[self.gen](rng, **self.gen_args)
+        return np.ascontiguousarray(ref, dtype=np.uint8), np.ascontiguousarray(query, dtype=np.uint8)
+
+
+# ------------------------------------------------------------------------------ generators
+def _indels(seq, rng, every):
+    """Short insertions/deletions about every `every` bases: bounds HSP length the way real
+    genomes do (a substitution-only homolog is one genome-long diagonal)."""
+    cuts = np.sort(rng.choice(np.arange(1, seq.size - 1), size=max(1, seq.size // every), replace=False))
+    parts, prev = [], 0
+    for c in cuts:
+        parts.append(seq[prev:c])
+        k = int(rng.integers(1, 12))
+        if rng.random() < 0.5:
+            parts.append(genome.random_genome(k, rng))
+            prev = c
+        else:
+            prev = min(seq.size, c + k)
+    parts.append(seq[prev:])
+    return np.concatenate(parts)
+
+
+def _homolog(rng, n, d, inversions=0, inv_len=0, indel_every=1500):
+    ref = genome.random_genome(n, rng)
+    q = genome.mutate(ref, d, rng)
+    if indel_every:
+        q = _indels(q, rng, indel_every)
+        n = min(n, q.size)
+    for s in (rng.integers(0, max(1, n - inv_len), size=inversions) if inversions else []):
+        q[s:s + inv_len] = genome.revcomp_ascii(q[s:s + inv_len])
+    return ref, q
+
+
+def gen_diverged(rng, n=200_000, d=0.25, inversions=2, inv_len=20_000):
+    return _homolog(rng, n, d, inversions, inv_len)
+
+
+def gen_self(rng, n=30_000):
+    ref = genome.random_genome(n, rng)
+    return ref, ref.copy()
+
+
+def gen_masked_multichrom(rng, n=300_000, d=0.2, chroms=4, f_mask=0.15, n_runs=3, n_len=500):
+    """Several chromosomes joined by '&', soft-masked runs, N runs (A.1, App. C L/N/E rows)."""
+    ref, q = _homolog(rng, n, d, 2, 15_000)
+    ref = genome.soft_mask(ref, f_mask, rng)
+    q = genome.soft_mask(q, f_mask, rng)
+    ref = genome.insert_runs(ref, b"N", n_runs, n_len, rng)
+    q = genome.insert_runs(q, b"N", n_runs, n_len, rng)
+    cut_r = np.sort(rng.integers(1, n - 1, size=chroms - 1))
+    cut_q = np.sort(rng.integers(1, n - 1, size=chroms - 1))
+    rb = genome.make_blocks(np.split(ref, cut_r), block_size=10 ** 12)
+    qb = genome.make_blocks(np.split(q, cut_q), block_size=10 ** 12)
+    return rb[0], qb[0]
+
+
+def gen_shared_ambiguous(rng, n=150_000, d=0.18, runs=60, run_len=6, query_iupac=False):
+    """Short N / IUPAC runs at the SAME places in ref and query so that N-N and X-X cells sit
+    inside HSPs under --ambiguous=iupac (the count[] aliasing of SURVEY A.6).  IUPAC letters in
+    the query require strand="plus": the reference's host RevComp drops them (ntcoding.cpp:63-105)
+    so its minus-strand seed positions no longer match the device's rev-comp block."""
+    ref = genome.random_genome(n, rng)
+    q = genome.mutate(ref, d, rng)
+    for s in rng.integers(0, n - run_len, size=runs):
+        ref[s:s + run_len] = ord("N")
+        q[s:s + run_len] = ord("N")
+    for s in rng.integers(0, n - run_len, size=runs):
+        ref[s:s + 2] = ord("R")
+        q[s:s + 2] = ord("R") if query_iupac else ord("N")
+    return ref, _indels(q, rng, 1500)
+
+
+def gen_repeats(rng, n=200_000, d=0.3, copies=150, elem=300, elem_div=0.1, low_complexity=40):
+    """A repeat family (heavy buckets, many HSPs per diagonal neighbourhood) plus AT-rich
+    low-complexity islands whose HSPs fall in [hspthresh, 3*hspthresh] and get entropy-scaled."""
+    ref, q = _homolog(rng, n, d)
+    element = genome.random_genome(elem, rng)
+    for arr in (ref, q):
+        for s in rng.integers(0, n - elem, size=copies):
+            arr[s:s + elem] = genome.mutate(element, elem_div, rng)
+    at = np.frombuffer(b"AT", dtype=np.uint8)
+    for s in rng.integers(0, n - 200, size=low_complexity):
+        island = at[(rng.random(120) < 0.5).astype(np.uint8)]
+        ref[s:s + 120] = island
+        q[s:s + 120] = genome.mutate(island, 0.05, rng)
+    return ref, q
+
+
+def gen_random_pair(rng, n_ref=400_000, n_query=100_000):
+    """Unrelated sequences: only random hits, nothing passes (zero-anchor iterations)."""
+    return genome.random_genome(n_ref, rng), genome.random_genome(n_query, rng)
+
+
+GENERATORS = {
+    "diverged": gen_diverged,
+    "self": gen_self,
+    "masked_multichrom": gen_masked_multichrom,
+    "shared_ambiguous": gen_shared_ambiguous,
+    "repeats": gen_repeats,
+    "random_pair": gen_random_pair,
+}
+
+# Small cases: the CPU oracle finishes each in seconds.  Golden dumps of the UNMODIFIED
+# reference for all of them are produced on a B200 by tests/golden/make_golden.py.
+CASES = [
+    Case("diverged_default", "diverged"),
+    Case("diverged_chunked", "diverged", dict(n=120_000, d=0.2), rng_seed=11, wga_chunk=20_000,
+         lastz_interval=50_000),
+    Case("diverged_multi_iter", "diverged", dict(n=150_000, d=0.22), rng_seed=12, max_hits_override=3000),
+    Case("self_align", "self"),
+    Case("masked_multichrom", "masked_multichrom"),
+    Case("iupac_notransition", "shared_ambiguous", dict(query_iupac=True), transition=False,
+         ambiguous="iupac", hspthresh=2200, strand="plus"),
+    Case("iupac_both_strands", "shared_ambiguous", rng_seed=6, ambiguous="iupac", hspthresh=2200),
+    Case("ambiguous_n", "shared_ambiguous", rng_seed=5, ambiguous="n", hspthresh=2500),
+    Case("repeats_entropy", "repeats"),
+    Case("repeats_noentropy", "repeats", rng_seed=7, noentropy=True),
+    Case("seed_14of22_notransition", "diverged", dict(n=250_000, d=0.15), rng_seed=21,
+         seed_shape="14of22", transition=False),
+    Case("step2", "diverged", dict(n=150_000, d=0.15), rng_seed=22, step=2),
+    Case("custom_seed_plus_only", "diverged", dict(n=100_000, d=0.2), rng_seed=23,
+         seed_shape="1110100110010101111", strand="plus"),
+    Case("minus_only_low_thresh", "diverged", dict(n=80_000, d=0.3), rng_seed=24, strand="minus",
+         hspthresh=1800, xdrop=600),
+    Case("random_pair", "random_pair"),
+]
+CASES_BY_NAME = {c.name: c for c in CASES}
+
+
+# ------------------------------------------------------------------------------ file formats
+def matrix_for(case: Case) -> np.ndarray:
+    from oracle import sa_oracle_py as sao
+    return sao.build_matrix(case.ambiguous, case.xdrop)
+
+
+def write_case_file(case: Case, path: Path, ref=None, query=None) -> None:
+    """SACASE01, read by oracle/ref_driver.cpp:read_case."""
+    if ref is None:
+        ref, query = case.inputs()
+    strand = {"both": 0, "plus": 1, "minus": 2}[case.strand]
+    shape = case.seed_shape.encode()
+    with open(path, "wb") as f:
+        f.write(b"SACASE01")
+        f.write(struct.pack("<I", len(shape)) + shape)
+        f.write(struct.pack("<iIiiiIIii", int(case.transition), case.step, case.xdrop, case.hspthresh,
+                            int(case.noentropy), case.wga_chunk, case.lastz_interval,
+                            case.max_hits_override, strand))
+        f.write(matrix_for(case).astype("<i4").tobytes())
+        f.write(struct.pack("<Q", ref.size) + ref.tobytes())
+        f.write(struct.pack("<Q", query.size) + query.tobytes())
+
+
+@dataclass
+class Dump:
+    calls: list           # [(rev, chunk_start, chunk_end, num_seeds, total_anchors, num_hits, segs)]
+    times: np.ndarray     # ref_upload, table, query_upload, seedgen, seed_and_filter (s)
+    counters: np.ndarray  # seeds, hits, hsps, device MAX_HITS
+    table: tuple | None = None
+
+
+def read_dump(path: Path) -> Dump:
+    """SAOUT001, written by oracle/ref_driver.cpp."""
+    b = Path(path).read_bytes()
+    assert b[:8] == b"SAOUT001", "bad dump magic"
+    off = 8
+    (ncalls,) = struct.unpack_from("<I", b, off); off += 4
+    calls = []
+    for _ in range(ncalls):
+        rev, cs, ce, ns, nseg, tot, nh = struct.unpack_from("<7I", b, off); off += 28
+        segs = np.frombuffer(b, dtype=SEGMENT_DTYPE, count=nseg, offset=off).copy(); off += 16 * nseg
+        calls.append((rev, cs, ce, ns, tot, nh, segs))
+    times = np.frombuffer(b, dtype="<f8", count=5, offset=off).copy(); off += 40
+    counters = np.frombuffer(b, dtype="<u8", count=4, offset=off).copy(); off += 32
+    (has_table,) = struct.unpack_from("<I", b, off); off += 4
+    table = None
+    if has_table:
+        isz, npos = struct.unpack_from("<II", b, off); off += 8
+        idx = np.frombuffer(b, dtype="<u4", count=isz, offset=off).copy(); off += 4 * isz
+        pos = np.frombuffer(b, dtype="<u4", count=npos, offset=off).copy(); off += 4 * npos
+        table = (idx, pos)
+    return Dump(calls, times, counters, table)
+
+
+def run_runner(binary: Path, case: Case, workdir: Path, extra=()) -> Dump:
+    workdir.mkdir(parents=True, exist_ok=True)
+    cf, of = workdir / f"{case.name}.case", workdir / f"{case.name}.{binary.name}.out"
+    write_case_file(case, cf)
+    subprocess.run([str(binary), str(cf), str(of), *extra], check=True, stderr=subprocess.PIPE)
+    return read_dump(of)
+
+
+# ------------------------------------------------------------------------------ golden fixtures
+def golden_path(case: Case) -> Path:
+    return GOLDEN_DIR / f"{case.name}.npz"
+
+
+def inputs_digest(ref: np.ndarray, query: np.ndarray) -> str:
+    h = hashlib.sha256()
+    h.update(ref.tobytes()); h.update(b"|"); h.update(query.tobytes())
+    return h.hexdigest()
+
+
+def save_golden(case: Case, dump: Dump, ref, query) -> None:
+    """Compact fixture: call headers + concatenated segments + input digest.  The inputs are
+    re-generated from the case's RNG seed and checked against the digest."""
+    hdr = np.array([(c[0], c[1], c[2], c[3], c[4], c[5], c[6].size) for c in dump.calls], dtype=np.uint32).reshape(-1, 7)
+    segs = np.concatenate([c[6] for c in dump.calls]) if dump.calls else np.empty(0, SEGMENT_DTYPE)
+    np.savez_compressed(golden_path(case), hdr=hdr, segs=segs.view(np.uint32).reshape(-1, 4),
+                        digest=np.array(inputs_digest(ref, query)), max_hits_device=dump.counters[3])
+
+
+def load_golden(case: Case):
+    z = np.load(golden_path(case))
+    hdr = z["hdr"]
+    segs = np.ascontiguousarray(z["segs"]).view(SEGMENT_DTYPE).reshape(-1)
+    calls, off = [], 0
+    for rev, cs, ce, ns, tot, nh, nseg in hdr:
+        calls.append((int(rev), int(cs), int(ce), int(ns), int(tot), int(nh), segs[off:off + nseg]))
+        off += int(nseg)
+    return calls, str(z["digest"])
+
+
+# ------------------------------------------------------------------------------ runners
+def chunk_calls(case: Case, q_len: int, span: int):
+    return genome.chunk_list(q_len, span, case.strand, case.lastz_interval, case.wga_chunk)
+
+
+def run_cpu_oracle(case: Case, ref=None, query=None, max_hits_device: int = 0xFFFFFFFF):
+    """The whole case through oracle/sa_oracle.c.  Returns [(rev, j0, j1, num_seeds, segs_with_header)]."""
+    from oracle import sa_oracle_py as sao
+    if ref is None:
+        ref, query = case.inputs()
+    shape = sao.Shape(case.seed_shape)
+    table = sao.Table(shape, ref, ref.size, case.step)
+    ref_enc = sao.encode(ref)
+    q_fwd, q_rc = sao.encode_rc(query)
+    q_rc_ascii = sao.revcomp_ascii(query)
+    mh = case.max_hits_override if case.max_hits_override > 0 else max_hits_device
+    params = sao.make_params(matrix_for(case), case.xdrop, case.hspthresh, case.noentropy, shape.span, mh)
+    out = []
+    for rev, j0, j1 in chunk_calls(case, query.size, shape.span):
+        seeds = shape.chunk_seeds(q_rc_ascii if rev else query, j0, j1, case.transition)
+        if seeds.size == 0:
+            continue
+        res = sao.seed_and_filter(params, table, ref_enc, q_rc if rev else q_fwd, seeds)
+        out.append((rev, j0, j1, seeds.size, res))
+    return out
+
+
+def setup_backend(be, case: Case, ref, query, buffer: int = 0):
+    """InitializeProcessor ... SendQueryWriteRequest in the order of src/main.cpp:297-298,:613-661."""
+    from segalign_b200.backend import shape_pattern
+    weight = be.GenerateShapePos(case.seed_shape)
+    span = len(shape_pattern(case.seed_shape))
+    be.InitializeProcessor(case.transition, case.wga_chunk, span, matrix_for(case), case.xdrop,
+                           case.hspthresh, case.noentropy)
+    if case.max_hits_override > 0:
+        be.set_max_hits(case.max_hits_override)
+    be.SendRefWriteRequest(ref, 0, ref.size)
+    be.GenerateSeedPosTable(ref, 0, ref.size, case.step)
+    be.SendQueryWriteRequest(query, 0, query.size, buffer)
+    return span, weight
+
+
+def run_backend(be, case: Case, ref=None, query=None, device_seeding: bool = False):
+    """The whole case through the CUDA backend (C ABI).  Same return layout as run_cpu_oracle."""
+    from segalign_b200.backend import shape_pattern
+    if ref is None:
+        ref, query = case.inputs()
+    span, _ = setup_backend(be, case, ref, query)
+    pattern = shape_pattern(case.seed_shape)
+    q_rc_ascii = genome.revcomp_ascii(query)
+    out = []
+    try:
+        for rev, j0, j1 in chunk_calls(case, query.size, span):
+            if device_seeding:
+                res, ns = be.SeedAndFilterRange(j0, j1, case.transition, bool(rev), 0)
+                if ns == 0:
+                    continue
+            else:
+                seeds = genome.chunk_seeds(q_rc_ascii if rev else query, j0, j1, pattern, case.transition)
+                if seeds.size == 0:
+                    continue
+                ns = seeds.size
+                res = be.SeedAndFilter(seeds, bool(rev), 0)
+            out.append((rev, j0, j1, ns, res))
+    finally:
+        be.ClearQuery(0)
+        be.ClearRef()
+        be.ShutdownProcessor()
+    return out
+
+
+def assert_calls_equal(got, want, what: str):
+    """got/want: lists of (rev, j0, j1, num_seeds, segs_with_header)."""
+    assert len(got) == len(want), f"{what}: {len(got)} calls vs {len(want)}"
+    for g, w in zip(got, want):
+        assert tuple(g[:4]) == tuple(w[:4]), f"{what}: call key {g[:4]} vs {w[:4]}"
+        gs, ws = g[4], w[4]
+        assert gs[0]["len"] == ws[0]["len"] and gs[0]["score"] == ws[0]["score"], \
+            f"{what}: header of call {g[:3]}: anchors/hits {gs[0]['len']}/{gs[0]['score']} vs {ws[0]['len']}/{ws[0]['score']}"
+        assert gs.size == ws.size, f"{what}: call {g[:3]}: {gs.size - 1} HSPs vs {ws.size - 1}"
+        if not np.array_equal(gs[1:], ws[1:]):
+            bad = np.flatnonzero(gs[1:] != ws[1:])[:5]
+            raise AssertionError(f"{what}: call {g[:3]} differs at {bad}: {gs[1:][bad]} vs {ws[1:][bad]}")
+
+
+def golden_as_calls(case: Case):
+    """Golden dump -> the (rev, j0, j1, num_seeds, segs_with_header) layout."""
+    calls, digest = load_golden(case)
+    out = []
+    for rev, cs, ce, ns, tot, nh, segs in calls:
+        res = np.zeros(segs.size + 1, dtype=SEGMENT_DTYPE)
+        res[0]["len"], res[0]["score"] = tot, np.int32(np.uint32(nh).view(np.int32))
+        res[1:] = segs
+        out.append((rev, cs, ce, ns, res))
+    return out, digest
