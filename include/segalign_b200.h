@@ -112,6 +112,14 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
                              uint32_t buffer, sa_segment **out, uint32_t *out_count,
                              uint32_t *out_num_seeds);
 
+/* Host seed words of one chunk -- src/seeder.cpp:57-74 + common/ntcoding.cpp:43-61, for callers
+ * that keep the reference's seed-vector ABI.  seq + block_start is the ASCII block
+ * (query_DRAM->buffer or query_rc_DRAM->buffer), positions [j0, j1); out must hold
+ * (j1-j0)*(1+weight) words.  Uses the shape of sa_set_seed_shape.  Thread-safe.  Returns the
+ * number of words written. */
+size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uint32_t j1,
+                           int transition, uint64_t *out);
+
 /* ShutdownProcessor -- src/seed_filter.cu:932-940 */
 int sa_shutdown_processor(void);
 

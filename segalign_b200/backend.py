@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sa_send_ref", "sa_generate_seed_pos_table", "sa_clear_ref", "sa_send_query",
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
-    "sa_reset_stats", "sa_set_profiling", "sa_version",
+    "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds",
 ]
 
 
@@ -75,6 +75,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_debug_get_encoded.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32]
     lib.sa_get_stats.argtypes = [C.POINTER(SaStats)]
     lib.sa_set_profiling.argtypes = [C.c_int]
+    lib.sa_host_chunk_seeds.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
+    lib.sa_host_chunk_seeds.restype = C.c_size_t
     return lib
 
 
@@ -158,6 +160,20 @@ class Backend:
         self._check(self.lib.sa_seed_and_filter_range(q_start, q_end, int(transition), int(rev), buffer,
                                                       C.byref(out), C.byref(n), C.byref(ns)))
         return self._take(out, n), ns.value
+
+    def host_chunk_seeds(self, seq: np.ndarray, j0: int, j1: int, transition: bool,
+                         out: np.ndarray | None = None) -> np.ndarray:
+        """src/seeder.cpp:57-74 natively; `out` (uint64, >= (j1-j0)*(1+weight)) may be pinned."""
+        if out is None:
+            out = np.empty(max(1, (j1 - j0) * (1 + self.seed_weight)), dtype=np.uint64)
+        n = self.lib.sa_host_chunk_seeds(seq.ctypes.data, 0, j0, j1, int(transition), out.ctypes.data)
+        return out[:n]
+
+    def SeedAndFilterPtr(self, seeds_ptr: int, num_seeds: int, rev: bool, buffer: int) -> np.ndarray:
+        out, n = C.c_void_p(), C.c_uint32()
+        self._check(self.lib.sa_seed_and_filter(seeds_ptr, num_seeds, int(rev), buffer,
+                                                C.byref(out), C.byref(n)))
+        return self._take(out, n)
 
     def ShutdownProcessor(self) -> None:
         self._check(self.lib.sa_shutdown_processor())

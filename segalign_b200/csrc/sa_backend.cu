@@ -133,7 +133,7 @@ struct Global {
     // stats
     std::mutex stats_mu;
     sa_stats stats = {};
-    bool profiling = false;
+    bool profiling = true; // per-phase CUDA events: two async records per phase, read after the call's final sync
 };
 
 Global G;
@@ -769,5 +769,36 @@ int sa_reset_stats(void) {
     return SA_OK;
 }
 int sa_set_profiling(int enabled) { G.profiling = enabled != 0; return SA_OK; }
+
+// Host-side seed words of one chunk, the loop of src/seeder.cpp:57-74 with
+// GetKmerIndexAtPos (common/ntcoding.cpp:43-61) restated as a rolling validity window.
+// Pure host code (no CUDA): it exists so that callers that still hand over seed vectors
+// (the reference ABI) can build them at memory speed from many threads.
+size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uint32_t j1,
+                           int transition, uint64_t *out) {
+    if (!G.shape_set || !seq || !out || j1 <= j0) return 0;
+    const ShapeDesc sh = G.shape;
+    const int span = sh.span, w = sh.weight;
+    const unsigned char *s = reinterpret_cast<const unsigned char *>(seq) + block_start;
+    static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
+    size_t n = 0;
+    // last_bad = index of the most recent non-ACGT character seen in [j0, j+span)
+    int64_t last_bad = -1;
+    for (uint32_t i = j0; i + 1 < j0 + (uint32_t)span && i < j1 + (uint32_t)span - 1; i++)
+        if (lut.v[s[i]] > 3) last_bad = i;
+    for (uint32_t j = j0; j < j1; j++) {
+        uint32_t tail = j + (uint32_t)span - 1;
+        if (lut.v[s[tail]] > 3) last_bad = tail;
+        if (last_bad >= (int64_t)j) continue;
+        uint64_t kmer = 0;
+        for (int i = 0; i < w; i++) kmer = (kmer << 2) | lut.v[s[j + sh.pos[i]]];
+        out[n++] = (kmer << 32) + j;
+        if (transition) {
+            for (int t = 0; t < w; t++)
+                if (sh.trans[t]) out[n++] = ((kmer ^ ((uint64_t)2 << (2 * t))) << 32) + j;
+        }
+    }
+    return n;
+}
 
 } // extern "C"

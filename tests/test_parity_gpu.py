@@ -1,0 +1,176 @@
+"""Parity tests proper: the CUDA backend, called through the C ABI, against (i) the golden dumps
+of the UNMODIFIED reference backend, (ii) the CPU oracle on fresh seeded inputs, and (iii)
+size-independent properties at sizes the oracle cannot reach.  Bit-exact everywhere."""
+import threading
+
+import numpy as np
+import pytest
+
+from tests import harness as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+def test_backend_matches_reference_golden(backend, case):
+    want, digest = H.golden_as_calls(case)
+    ref, query = case.inputs()
+    assert H.inputs_digest(ref, query) == digest
+    got = H.run_backend(backend, case, ref, query)
+    H.assert_calls_equal(got, want, "backend vs reference golden")
+
+
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+def test_device_seeding_matches_reference_golden(backend, case):
+    """sa_seed_and_filter_range (seed words generated on the GPU) returns exactly what
+    the reference returns for the host-built seed vector of the same chunk."""
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=True)
+    H.assert_calls_equal(got, want, "device seeding vs reference golden")
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_backend_matches_cpu_oracle_fresh_inputs(backend, seed):
+    case = H.Case(f"fresh_{seed}", "masked_multichrom", dict(n=120_000, d=0.22), rng_seed=seed,
+                  wga_chunk=50_000, max_hits_override=40_000 if seed == 202 else 0)
+    ref, query = case.inputs()
+    want = H.run_cpu_oracle(case, ref, query, max_hits_device=748058112)
+    got = H.run_backend(backend, case, ref, query)
+    H.assert_calls_equal(got, want, "backend vs cpu oracle")
+
+
+def test_encoding_matches_oracle(backend):
+    from oracle import sa_oracle_py as sao
+    rng = np.random.default_rng(5)
+    for n in (1, 15, 16, 17, 31, 32, 33, 1000, 100_003):
+        seq = rng.choice(np.frombuffer(b"ACGTacgtNn&RYKM-", dtype=np.uint8), size=n)
+        case = H.Case("enc", "random_pair")
+        backend.GenerateShapePos("12of19")
+        backend.InitializeProcessor(True, 1000, 19, H.matrix_for(case), 910, 3000, False)
+        backend.SendRefWriteRequest(seq, 0, n)
+        backend.SendQueryWriteRequest(seq, 0, n, 1)
+        fwd, rc = sao.encode_rc(seq)
+        assert np.array_equal(backend.get_encoded(0, 0, n), sao.encode(seq))
+        assert np.array_equal(backend.get_encoded(1, 1, n), fwd)
+        assert np.array_equal(backend.get_encoded(2, 1, n), rc)
+        backend.ClearQuery(1)
+        backend.ClearRef()
+        backend.ShutdownProcessor()
+        backend.InitializeInterface(1)
+
+
+@pytest.mark.parametrize("shape,step", [("12of19", 1), ("12of19", 3), ("14of22", 1), ("110101011", 2)])
+def test_seed_position_table_matches_oracle(backend, shape, step):
+    """index_table identical; pos_table identical as per-bucket multisets (order inside a bucket
+    is scheduling-dependent in the reference)."""
+    from oracle import sa_oracle_py as sao
+    from tests.harness import genome
+    rng = np.random.default_rng(8)
+    ref = genome.soft_mask(genome.random_genome(300_000, rng), 0.2, rng)
+    ref = genome.insert_runs(ref, b"N", 3, 400, rng)
+    ref[1234] = ord("&")
+    sh = sao.Shape(shape)
+    backend.GenerateShapePos(shape)
+    backend.InitializeProcessor(True, 1000, sh.span, H.matrix_for(H.Case("t", "random_pair")), 910, 3000, False)
+    backend.SendRefWriteRequest(ref, 0, ref.size)
+    backend.GenerateSeedPosTable(ref, 0, ref.size, step)
+    idx, pos = backend.get_table()
+    tab = sao.Table(sh, ref, ref.size, step)
+    assert np.array_equal(idx, tab.index)
+    assert pos.size == tab.pos.size
+    starts = np.concatenate([[0], idx[:-1]]).astype(np.int64)
+    bucket = np.repeat(np.arange(idx.size, dtype=np.int64), idx.astype(np.int64) - starts)
+    assert np.array_equal(pos[np.lexsort((pos, bucket))], tab.pos[np.lexsort((tab.pos, bucket))])
+    backend.ClearRef()
+
+
+def _big_case():
+    return H.Case("big", "masked_multichrom", dict(n=3_000_000, d=0.3, chroms=3, f_mask=0.1), rng_seed=77)
+
+
+def test_properties_at_scale(backend):
+    """3 Mb x 3 Mb (beyond what the CPU oracle does in seconds): per-call output is sorted by
+    hspCompLastz within each iteration, survives its own sort+dedupe unchanged (idempotence, via
+    the oracle's sort_dedupe), every HSP re-extends to itself from its own start, and repeated /
+    concurrent calls return identical bytes."""
+    from oracle import sa_oracle_py as sao
+    case = _big_case()
+    ref, query = case.inputs()
+    span, _ = H.setup_backend(backend, case, ref, query)
+    units = H.chunk_calls(case, query.size, span)
+    outs = [backend.SeedAndFilterRange(j0, j1, True, bool(rev), 0)[0] for rev, j0, j1 in units]
+    total = sum(o.size - 1 for o in outs)
+    assert total > 500
+    for o in outs:
+        assert o[0]["len"] == o.size - 1
+        segs = o[1:]
+        if segs.size < 2:
+            continue
+        # at most two iterations (A.7): a sorted run, optionally followed by a second sorted run
+        key = segs["query_start"].astype(np.int64)
+        assert (np.diff(key) < 0).sum() <= 1
+        # dedupe idempotence on the first run
+        cut = int(np.argmax(np.diff(key) < 0)) + 1 if (np.diff(key) < 0).any() else segs.size
+        assert np.array_equal(sao.sort_dedupe(segs[:cut]), segs[:cut])
+    # checksum of checksums: repeat sequentially and from 4 threads
+    def checksum(arrs):
+        return [hash(a[1:].tobytes()) for a in arrs]
+    base = checksum(outs)
+    again = [None] * len(units)
+
+    def work(tid):
+        for i in range(tid, len(units), 4):
+            rev, j0, j1 = units[i]
+            again[i] = backend.SeedAndFilterRange(j0, j1, True, bool(rev), 0)[0]
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert checksum(again) == base
+    # spot-check 200 HSPs against the CPU oracle's single-hit extension: extending from the
+    # HSP's own last cell + 1 ... is not an invariant, but scoring the segment is:
+    sub = H.matrix_for(case).reshape(8, 8)
+    ref_enc = sao.encode(ref)
+    q_fwd, q_rc = sao.encode_rc(query)
+    rng = np.random.default_rng(0)
+    checked = 0
+    for (rev, j0, j1), o in zip(units, outs):
+        q = q_rc if rev else q_fwd
+        for s in o[1:][rng.permutation(o.size - 1)[:20]]:
+            r0, q0, n = int(s["ref_start"]), int(s["query_start"]), int(s["len"]) + 1
+            raw = int(sub[ref_enc[r0:r0 + n], q[q0:q0 + n]].sum())
+            assert raw >= case.hspthresh and s["score"] <= raw
+            assert s["score"] == raw or raw <= 3 * case.hspthresh  # only entropy may lower it
+            checked += 1
+    assert checked > 100
+    backend.ClearQuery(0)
+    backend.ClearRef()
+
+
+def test_vector_abi_equals_device_seeding_at_scale(backend):
+    case = H.Case("big2", "diverged", dict(n=1_500_000, d=0.3), rng_seed=78)
+    ref, query = case.inputs()
+    a = H.run_backend(backend, case, ref, query, device_seeding=False)
+    backend.InitializeInterface(1)
+    b = H.run_backend(backend, case, ref, query, device_seeding=True)
+    H.assert_calls_equal(a, b, "vector ABI vs device seeding")
+
+
+def test_state_errors(backend):
+    from segalign_b200.backend import BackendError
+    with pytest.raises(BackendError) as ei:
+        backend.SeedAndFilter(np.array([1], dtype=np.uint64), False, 0)
+    assert ei.value.code == -21
+    backend.GenerateShapePos("12of19")
+    backend.InitializeProcessor(True, 100, 19, H.matrix_for(H.Case("t", "random_pair")), 910, 3000, False)
+    seq = np.frombuffer(b"ACGT" * 100, dtype=np.uint8)
+    backend.SendRefWriteRequest(seq, 0, seq.size)
+    backend.GenerateSeedPosTable(seq, 0, seq.size, 1)
+    backend.SendQueryWriteRequest(seq, 0, seq.size, 0)
+    with pytest.raises(BackendError) as ei:  # MAX_SEEDS exceeded (seed_filter.cu:688-692)
+        backend.SeedAndFilter(np.zeros(13 * 100 + 1, dtype=np.uint64), False, 0)
+    assert ei.value.code == -20
+    with pytest.raises(BackendError):
+        backend.SendQueryWriteRequest(seq, 0, seq.size, 2)  # BUFFER_DEPTH = 2
+    # empty and header-only results
+    out = backend.SeedAndFilter(np.empty(0, dtype=np.uint64), False, 0)
+    assert out.size == 1 and out[0]["len"] == 0 and out[0]["score"] == 0
