@@ -26,7 +26,11 @@
 #include "ntcoding.h"
 #include "seed_filter_interface.h"
 #include "seed_filter.h"
+#ifndef NEW_BACKEND
 #include "store_gpu.h"
+#else
+#include "segalign_b200.h" // new_runner: same driver, B200 backend behind the reference's symbols
+#endif
 
 // globals the reference objects expect from main.cpp (main.cpp:26-54)
 Configuration cfg;
@@ -46,8 +50,10 @@ std::vector<uint32_t> r_chr_file_name;
 std::vector<size_t> r_chr_start;
 std::vector<uint32_t> r_chr_len;
 
+#ifndef NEW_BACKEND
 extern int MAX_HITS;  // src/seed_filter.cu:21 (non-static global)
 extern int MAX_SEEDS; // src/seed_filter.cu:20
+#endif
 
 struct CaseFile {
     std::string seed_shape;
@@ -143,8 +149,14 @@ int main(int argc, char **argv) {
     cfg.num_gpu = g_InitializeInterface(1);
     g_InitializeProcessor(cfg.seed.transition, cfg.wga_chunk_size, cfg.seed.size, cfg.sub_mat,
                           cfg.xdrop, cfg.hspthresh, cfg.noentropy);
+#ifndef NEW_BACKEND
     int ref_max_hits = MAX_HITS;
     if (c.max_hits_override > 0) MAX_HITS = c.max_hits_override;
+#else
+    int ref_max_hits = (int)sa_get_max_hits();
+    if (c.max_hits_override > 0) sa_set_max_hits((uint32_t)c.max_hits_override);
+    int MAX_HITS = (int)sa_get_max_hits();
+#endif
     ref_DRAM = new DRAM;
     query_DRAM = new DRAM;
     query_rc_DRAM = new DRAM;
@@ -289,10 +301,17 @@ int main(int argc, char **argv) {
     if (dump_table) {
         uint32_t index_size = (uint32_t)1 << (2 * cfg.seed.kmer_size);
         std::vector<uint32_t> idx(index_size);
+#ifndef NEW_BACKEND
         cudaMemcpy(idx.data(), d_index_table[0], (size_t)index_size * 4, cudaMemcpyDeviceToHost);
         uint32_t num_pos = idx[index_size - 1];
         std::vector<uint32_t> pos(num_pos ? num_pos : 1);
         cudaMemcpy(pos.data(), d_pos_table[0], (size_t)num_pos * 4, cudaMemcpyDeviceToHost);
+#else
+        uint32_t num_pos = 0;
+        sa_debug_get_table(&index_size, &num_pos, nullptr, nullptr);
+        std::vector<uint32_t> pos(num_pos ? num_pos : 1);
+        sa_debug_get_table(&index_size, &num_pos, idx.data(), pos.data());
+#endif
         fwrite(&index_size, 4, 1, o);
         fwrite(&num_pos, 4, 1, o);
         fwrite(idx.data(), 4, index_size, o);

@@ -261,10 +261,14 @@ __device__ __forceinline__ uint32_t iteration_of(const uint32_t *__restrict__ hi
     return lo;
 }
 
-// counters[0] = anchor cursor, counters[1..2] = ext_cells (64-bit)
+// counters[0] = anchor cursor, counters[2..3] = ext_cells (64-bit), counters[4] = survivor count.
+// With surv != nullptr the kernel walks the survivor list of the filter kernel (hit indices,
+// count read from counters[4] on the device so the host need not synchronise in between);
+// otherwise it walks hits [h_begin, h_end) directly.
 __global__ void __launch_bounds__(128)
 k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              uint32_t h_begin, uint32_t h_end, const uint32_t *__restrict__ hit_bound,
+              uint32_t h_begin, uint32_t h_end, const uint32_t *__restrict__ surv,
+              const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors,
               uint32_t anchor_cap, uint32_t *__restrict__ counters) {
     __shared__ int sub[64];
@@ -276,7 +280,9 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x;
     unsigned long long cells = 0;
-    for (uint32_t h = h_begin + blockIdx.x * blockDim.x + threadIdx.x; h < h_end; h += stride) {
+    if (surv) { h_begin = 0; h_end = counters[4]; }
+    for (uint32_t i = h_begin + blockIdx.x * blockDim.x + threadIdx.x; i < h_end; i += stride) {
+        const uint32_t h = surv ? surv[i] : i;
         uint2 hit = hits[h];
         sa_segment seg;
         if (extend_hit(P, sub, lut16, diag, hit.x, hit.y, &seg, &cells)) {
@@ -292,7 +298,7 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
             }
         }
     }
-    if (cells) atomicAdd(reinterpret_cast<unsigned long long *>(counters + 2), cells);
+    if (cells && !surv) atomicAdd(reinterpret_cast<unsigned long long *>(counters + 2), cells);
 }
 
 } // namespace sa

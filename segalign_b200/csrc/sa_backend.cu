@@ -22,6 +22,7 @@
 
 #include "kernels_encode.cuh"
 #include "kernels_extend.cuh"
+#include "kernels_filter.cuh"
 #include "kernels_lookup.cuh"
 #include "kernels_sort.cuh"
 #include "sa_common.cuh"
@@ -83,7 +84,7 @@ int ensure(T *&ptr, size_t &cap, size_t need, const char *tag, size_t slack_num 
 struct Workspace {
     int gpu = 0; // index into G.gpus
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[10] = {};
+    cudaEvent_t ev[10] = {}; // indexed by Phase
     uint64_t *d_seeds = nullptr; size_t seeds_cap = 0;
     uint32_t *d_prefix = nullptr; size_t prefix_cap = 0;
     uint32_t *d_limit_pos = nullptr; size_t limit_cap = 0;
@@ -91,6 +92,7 @@ struct Workspace {
     uint32_t *d_plan = nullptr;      // [0]=num_iter [1]=num_hits
     uint32_t *d_counters = nullptr;  // [0]=anchor cursor [1]=dedupe cursor [2..3]=ext cells
     uint2 *d_hits = nullptr; size_t hits_cap = 0;
+    uint32_t *d_surv = nullptr; size_t surv_cap = 0; // filter survivors (hit indices)
     Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
     Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
     sa_segment *d_out = nullptr; size_t out_cap = 0;
@@ -119,6 +121,10 @@ struct Global {
     uint32_t max_seeds = 0, max_hits = 0, max_hits_device = 0, seed_size = 0;
     int sub_mat[64] = {};
     int xdrop = 0, hspthresh = 0, noentropy = 0, diag_all_positive = 0, transition = 0;
+    uint32_t term_codes = 0;   // non-ACGT codes that always trip the X-drop rule (kernels_filter.cuh)
+    bool filter_ok = false;    // ACGT x ACGT scores fit int8: the filter stage is usable
+    bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
+    int filter_grid = 0;
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
     uint32_t query_len[SA_BUFFER_DEPTH] = {};
@@ -148,6 +154,7 @@ int free_planes(SeqPlanes &p) {
     if (p.b8) CU(cudaFree(p.b8), SA_ERR_FREE);
     if (p.p2) CU(cudaFree(p.p2), SA_ERR_FREE);
     if (p.m1) CU(cudaFree(p.m1), SA_ERR_FREE);
+    if (p.rec_base) CU(cudaFree(p.rec_base), SA_ERR_FREE);
     p = SeqPlanes();
     return SA_OK;
 }
@@ -158,10 +165,19 @@ int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag) {
     cudaError_t e = cudaMalloc((void **)&p.b8, (size_t)len + 64);
     if (e == cudaSuccess) e = cudaMalloc((void **)&p.p2, p.words * sizeof(uint64_t));
     if (e == cudaSuccess) e = cudaMalloc((void **)&p.m1, p.words * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p.rec_base, (p.words + REC_FRONT + 1) * sizeof(uint4));
+    p.rec = p.rec_base ? p.rec_base + REC_FRONT : nullptr;
     if (e != cudaSuccess)
         return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for %s failed with error \" %s \"",
                     (unsigned long)len, tag, cudaGetErrorString(e));
     return SA_OK;
+}
+
+// filter records of one block under the current terminator set (async on the control stream)
+void build_records(GpuCtx &g, SeqPlanes &p) {
+    k_pack_records<<<grid_for(p.words + REC_FRONT, 256), 256, 0, g.ctrl>>>(p.b8, p.len, p.rec, REC_FRONT,
+                                                                            (uint32_t)p.words, G.term_codes);
+    p.term_codes = G.term_codes;
 }
 
 // upload ASCII and encode; fwd always, rc if rc != nullptr
@@ -189,7 +205,9 @@ int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, 
     if (rc)
         k_pack_planes<<<grid_for(rc->words, 256), 256, 0, g.ctrl>>>(rc->b8, len, rc->p2, rc->m1,
                                                                      (uint32_t)rc->words);
-    add_launches(rc ? 3 : 2);
+    build_records(g, fwd);
+    if (rc) build_records(g, *rc);
+    add_launches(rc ? 5 : 3);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
     CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
     CU(cudaFree(d_tmp), SA_ERR_FREE);
@@ -236,7 +254,7 @@ int make_workspace(int gpu_index, Workspace *&out) {
 void destroy_workspace(Workspace *w) {
     cudaFree(w->d_seeds); cudaFree(w->d_prefix); cudaFree(w->d_limit_pos);
     cudaFree(w->d_hit_bound); cudaFree(w->d_plan); cudaFree(w->d_counters);
-    cudaFree(w->d_hits); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
+    cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
@@ -245,15 +263,20 @@ void destroy_workspace(Workspace *w) {
 }
 
 // ------------------------------------------------------------------ the per-call pipeline
+enum Phase { PH_START = 0, PH_SEEDS, PH_PLAN, PH_LOOKUP, PH_FILTER, PH_EXTEND, PH_SORT, PH_D2H, PH_COUNT };
 struct PhaseTimer {
     Workspace *w;
     bool on;
-    int n = 0;
+    bool have[PH_COUNT] = {};
     explicit PhaseTimer(Workspace *w_) : w(w_), on(G.profiling) {}
-    void mark() { if (on && n < 10) cudaEventRecord(w->ev[n++], w->stream); }
-    float ms(int a, int b) const {
+    void mark(Phase p) { if (on) { cudaEventRecord(w->ev[p], w->stream); have[p] = true; } }
+    // time between the latest recorded phase before b and b
+    float ms(Phase b) const {
+        if (!on || !have[b]) return 0.f;
+        int a = (int)b - 1;
+        while (a >= 0 && !have[a]) a--;
         float t = 0;
-        if (on && b < n) cudaEventElapsedTime(&t, w->ev[a], w->ev[b]);
+        if (a >= 0) cudaEventElapsedTime(&t, w->ev[a], w->ev[b]);
         return t;
     }
 };
@@ -274,7 +297,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
     GpuCtx &g = G.gpus[w->gpu];
     cudaStream_t st = w->stream;
     uint64_t launches = 0;
-    uint32_t num_hits = 0, num_iter = 0, n_pre = 0, n_final = 0;
+    uint32_t num_hits = 0, num_iter = 0, n_pre = 0, n_final = 0, n_surv = 0;
     unsigned long long ext_cells = 0;
 
     // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
@@ -298,7 +321,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
         TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
         TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
     }
-    pt.mark(); // [2] after count/scan/plan
+    pt.mark(PH_PLAN);
 
     if (num_hits > 0) {
         // 3. flat hit expansion (seed_filter.cu:760)
@@ -306,7 +329,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
         k_expand_hits<<<grid_for(((size_t)num_seeds + 31) / 32 * 32, 256), 256, 0, st>>>(
             w->d_seeds, num_seeds, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits);
         launches++;
-        pt.mark(); // [3] after lookup
+        pt.mark(PH_LOOKUP);
         // 4. extension + append (seed_filter.cu:762-774)
         ExtendParams P;
         const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
@@ -315,20 +338,35 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
         P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
         P.diag_all_positive = G.diag_all_positive;
         if (!w->d_anchors_a) TRY(ensure(w->d_anchors_a, w->anchors_a_cap, (size_t)1 << 20, "hsp_reduced", 1, 1));
-        for (;;) {
-            CU(cudaMemsetAsync(w->d_counters, 0, 8 * sizeof(uint32_t), st), SA_ERR_MEMCPY);
-            k_extend_hits<<<grid_for(num_hits, 128, 16), 128, 0, st>>>(
-                P, g.d_sub_mat, w->d_hits, 0u, num_hits, w->d_hit_bound, w->d_plan, w->d_anchors_a,
-                (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu), w->d_counters);
+        const bool filter = G.filter_ok && G.use_filter;
+        CU(cudaMemsetAsync(w->d_counters, 0, 8 * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        if (filter) {
+            // stage A: conservative score bound over all hits -> survivor list (kernels_filter.cuh)
+            TRY(ensure(w->d_surv, w->surv_cap, num_hits, "survivors"));
+            FilterParams F;
+            F.rrec = g.ref.rec; F.qrec = q.rec;
+            F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
+            k_filter_hits<<<G.filter_grid, FILTER_THREADS, FILTER_LUT_WORDS * sizeof(uint32_t), st>>>(
+                F, g.d_sub_mat, w->d_hits, num_hits, w->d_surv, w->d_counters);
             launches++;
-            CU(cudaMemcpyAsync(w->h_small, w->d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+            pt.mark(PH_FILTER);
+        }
+        for (;;) {
+            // stage B: exact extension (of the survivors, or of every hit without the filter)
+            k_extend_hits<<<grid_for(filter ? std::max<uint32_t>(num_hits / 64, 4096) : num_hits, 128, 16), 128, 0, st>>>(
+                P, g.d_sub_mat, w->d_hits, 0u, num_hits, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
+                w->d_anchors_a, (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu), w->d_counters);
+            launches++;
+            CU(cudaMemcpyAsync(w->h_small, w->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
             CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
             n_pre = w->h_small[0];
+            n_surv = filter ? w->h_small[4] : num_hits;
             memcpy(&ext_cells, &w->h_small[2], 8);
             if (n_pre <= w->anchors_a_cap) break;
-            TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced")); // rare: rerun
+            TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced")); // rare: rerun stage B
+            CU(cudaMemsetAsync(w->d_counters, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
         }
-        pt.mark(); // [4] after extension
+        pt.mark(PH_EXTEND);
         // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782)
         if (n_pre > 0) {
             TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
@@ -342,7 +380,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
             k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_b, n_final, w->d_out);
             launches += 8;
         }
-        pt.mark(); // [5] after sort
+        pt.mark(PH_SORT);
     }
     // 6. result (seed_filter.cu:786-788, :804-822)
     sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
@@ -360,7 +398,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
                         (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
         }
     }
-    pt.mark(); // [6] after D2H
+    pt.mark(PH_D2H);
     if (pt.on) CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
     *out = res;
@@ -368,21 +406,17 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
     {
         std::lock_guard<std::mutex> l(G.stats_mu);
         sa_stats &s = G.stats;
-        s.calls++; s.seeds += num_seeds; s.hits += num_hits; s.survivors += num_hits;
+        s.calls++; s.seeds += num_seeds; s.hits += num_hits; s.survivors += n_surv;
         s.anchors_pre_dedupe += n_pre; s.hsps += n_final; s.ext_cells += ext_cells;
         s.launches += launches;
         if (pt.on) {
-            // marks: 0 start, 1 after H2D/seed gen, 2 plan, [3 lookup, 4 extend, 5 sort], last d2h
-            s.ms_h2d += pt.ms(0, 1);
-            s.ms_count_scan += pt.ms(1, 2);
-            if (num_hits > 0) {
-                s.ms_lookup += pt.ms(2, 3);
-                s.ms_extend += pt.ms(3, 4);
-                s.ms_sort += pt.ms(4, 5);
-                s.ms_d2h += pt.ms(5, 6);
-            } else {
-                s.ms_d2h += pt.ms(2, 3);
-            }
+            s.ms_h2d += pt.ms(PH_SEEDS);
+            s.ms_count_scan += pt.ms(PH_PLAN);
+            s.ms_lookup += pt.ms(PH_LOOKUP);
+            s.ms_prefilter += pt.ms(PH_FILTER);
+            s.ms_extend += pt.ms(PH_EXTEND);
+            s.ms_sort += pt.ms(PH_SORT);
+            s.ms_d2h += pt.ms(PH_D2H);
         }
     }
     return SA_OK;
@@ -443,6 +477,21 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     G.noentropy = noentropy;
     memcpy(G.sub_mat, sub_mat, sizeof(G.sub_mat));
     G.diag_all_positive = sub_mat[0] > 0 && sub_mat[9] > 0 && sub_mat[18] > 0 && sub_mat[27] > 0;
+    // kernels_filter.cuh preconditions: int8 ACGT block; terminator codes = non-ACGT codes whose
+    // every entry is < -xdrop (the reference's X-drop rule then always fires on that cell)
+    G.filter_ok = true;
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++)
+            if (sub_mat[a * 8 + b] < -128 || sub_mat[a * 8 + b] > 127) G.filter_ok = false;
+    G.term_codes = 0;
+    for (int c = 4; c < 8; c++) {
+        bool term = true;
+        for (int d = 0; d < 8; d++)
+            if (sub_mat[c * 8 + d] >= -xdrop || sub_mat[d * 8 + c] >= -xdrop) term = false;
+        if (term) G.term_codes |= 1u << c;
+    }
+    const char *fenv = getenv("SEGALIGN_B200_FILTER");
+    G.use_filter = !(fenv && atoi(fenv) == 0);
     const char *env = getenv("SEGALIGN_B200_STREAMS");
     if (env && atoi(env) > 0) G.ws_per_gpu = atoi(env);
     for (size_t i = 0; i < G.gpus.size(); i++) {
@@ -450,6 +499,16 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
         CU(cudaMalloc((void **)&g.d_sub_mat, 64 * sizeof(int)), SA_ERR_MALLOC);
         CU(cudaMemcpy(g.d_sub_mat, sub_mat, 64 * sizeof(int), cudaMemcpyHostToDevice), SA_ERR_MEMCPY);
+        int per_sm = 0, sms = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_hits, FILTER_THREADS,
+                                                         FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
+        CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device), SA_ERR_KERNEL);
+        G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
+        // blocks uploaded before the matrix was known carry records built for another terminator set
+        SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
+        for (SeqPlanes *p : all)
+            if (p->rec && p->term_codes != G.term_codes) build_records(g, *p);
+        CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
         for (int k = 0; k < G.ws_per_gpu; k++) {
             Workspace *w = nullptr;
             TRY(make_workspace((int)i, w));
@@ -650,11 +709,11 @@ int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint3
     WsGuard guard(w);
     CU(cudaSetDevice(G.gpus[w->gpu].device), SA_ERR_SET_DEVICE);
     PhaseTimer pt(w);
-    pt.mark(); // [0]
+    pt.mark(PH_START);
     TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
     TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
     CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
-    pt.mark(); // [1]
+    pt.mark(PH_SEEDS);
     return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
 }
 
@@ -671,7 +730,7 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
     const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
     if (q_end > q.len) return fail(SA_ERR_ARG, "range [%u,%u) exceeds the query block (%u)", q_start, q_end, q.len);
     PhaseTimer pt(w);
-    pt.mark(); // [0]
+    pt.mark(PH_START);
     uint32_t n = q_end - q_start, num_seeds = 0;
     const uint32_t per = 1u + (transition ? (uint32_t)G.shape.num_trans : 0u);
     if (n > 0) {
@@ -706,7 +765,7 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
         *out = res; *out_count = 1;
         return SA_OK;
     }
-    pt.mark(); // [1]
+    pt.mark(PH_SEEDS);
     return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
 }
 

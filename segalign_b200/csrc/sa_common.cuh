@@ -6,6 +6,9 @@
 //        A,C,G,T = 0..3, every other symbol stored as 0
 //   m1 : 1 bit / base, 32 bases per uint32 word; 1 = "not an upper-case A/C/G/T"
 //        (codes L,N,X,E) and also 1 for every padding cell past the end of the block
+//   rec: 16 bytes / 32 bases = {p2 lo, p2 hi, terminator bits, soft bits}: what the filter kernel
+//        reads (one or two 16-byte loads per 32-cell window instead of four scalar loads from two
+//        planes); REC_FRONT records in front and PAD_WORDS behind are pure terminators
 // The hot kernels read only p2/m1 (0.375 byte per base instead of 1); b8 is touched by the
 // exact extension only inside 32-base tiles that contain a masked cell.
 #pragma once
@@ -21,12 +24,17 @@ constexpr uint8_t A_NT = 0, C_NT = 1, G_NT = 2, T_NT = 3, L_NT = 4, N_NT = 5, X_
 constexpr uint32_t INVALID_KMER = 1u << 31;
 constexpr int PAD_WORDS = 4; // padding words appended to p2/m1 (all masked)
 
+constexpr int REC_FRONT = 4; // padding records in front of record 0 (pure terminators)
+
 struct SeqPlanes {
     uint8_t *b8 = nullptr;
     uint64_t *p2 = nullptr;
     uint32_t *m1 = nullptr;
+    uint4 *rec_base = nullptr; // filter records {p2 lo, p2 hi, terminator bits, soft bits}, REC_FRONT + words
+    uint4 *rec = nullptr;      // = rec_base + REC_FRONT (record 0 = bases 0..31)
+    uint32_t term_codes = 0;   // terminator code set the records were built with
     uint32_t len = 0;
-    size_t words = 0; // p2/m1 words including padding
+    size_t words = 0; // p2/m1/rec words including back padding
 };
 
 // seed shape in constant-free form (passed by value to kernels)

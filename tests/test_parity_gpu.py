@@ -174,3 +174,23 @@ def test_state_errors(backend):
     # empty and header-only results
     out = backend.SeedAndFilter(np.empty(0, dtype=np.uint64), False, 0)
     assert out.size == 1 and out[0]["len"] == 0 and out[0]["score"] == 0
+
+
+@pytest.mark.parametrize("name", ["diverged_chunked", "masked_multichrom", "diverged_multi_iter", "repeats_entropy"])
+def test_dropin_runner_with_reference_host_objects(name, tmp_path, built):
+    """oracle/_ref/new_runner = the reference's own ntcoding.o, DRAM.o and seeder.o + the driver
+    that produced the golden dumps, linked against segalign_b200/csrc/shim.cpp (g_* symbols,
+    GenerateSeedPosTable) + libsegalign_b200.so instead of the reference's three .cu files.
+    --check-seeder additionally runs the reference's unmodified seeder_body functor on it."""
+    if not H.NEW_RUNNER.exists():
+        pytest.skip("oracle/_ref/new_runner not built (needs /root/reference at build time)")
+    case = H.CASES_BY_NAME[name]
+    dump = H.run_runner(H.NEW_RUNNER, case, tmp_path, extra=("--check-seeder", "--dump-table"))
+    want, _ = H.golden_as_calls(case)
+    got = []
+    for rev, cs, ce, ns, tot, nh, segs in dump.calls:
+        res = np.zeros(segs.size + 1, dtype=H.SEGMENT_DTYPE)
+        res[0]["len"], res[0]["score"] = tot, np.uint32(nh).view(np.int32)
+        res[1:] = segs
+        got.append((rev, cs, ce, ns, res))
+    H.assert_calls_equal(got, want, "new_runner (reference host objects + shim) vs reference golden")
