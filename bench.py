@@ -283,7 +283,7 @@ def run_ours(args):
                            "achieved": round((16.0 * st_res["seeds"] + 4.0 * st_res["hits"]) /
                                              max(1e-9, (st_res["ms_count_scan"] + st_res["ms_lookup"]) * 1e-3) / 1e9, 1)},
                 "phase_ms_per_step": {k: round(st_res[k] / args.steps, 3) for k in
-                                      ("ms_h2d", "ms_count_scan", "ms_lookup", "ms_extend", "ms_sort", "ms_d2h")},
+                                      ("ms_h2d", "ms_count_scan", "ms_lookup", "ms_prefilter", "ms_extend", "ms_sort", "ms_d2h")},
                 "note": "phase times are summed over concurrent streams (host_threads calls in flight)"}
 
     cpu_baseline = None
@@ -311,6 +311,8 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline,
             "clocks": clocks,
             "counters_per_step": {"seeds": st_res["seeds"] // args.steps, "hits": st_res["hits"] // args.steps,
+                                  "filter_survivors": st_res["survivors"] // args.steps,
+                                  "anchors_pre_dedupe": st_res["anchors_pre_dedupe"] // args.steps,
                                   "hsps": hsps_res // args.steps,
                                   "ext_cells_beyond_64": st_res["ext_cells"] // args.steps},
             "setup_ms": {"ref_upload_encode": round((t1 - t0) * 1e3, 1), "seed_pos_table_build": round((t2 - t1) * 1e3, 1),

@@ -44,6 +44,10 @@ struct FilterParams {
     int xdrop;
     int hspthresh;
     int diag_all_positive;
+    // loop constants handed over as kernel parameters so that they are read from the constant
+    // bank as instruction operands (as immediates ptxas re-materialises them in every group)
+    uint32_t k_mul; // 8 | 128 << 8 : dp2a multipliers
+    uint32_t k_m4;  // 0x01010101   : dp4a selector of the full group
 };
 
 // counters layout shared with the host (uint32 words)
@@ -78,17 +82,31 @@ __device__ __forceinline__ int diag_sum32_f(uint64_t win, const int *diag) {
     return nA * diag[0] + nC * diag[1] + nG * diag[2] + nT * diag[3];
 }
 
-// One 4-cell group: rb/qb hold the group's 8 bits of ref / query codes in bits 0..7.
-// Returns true if the walk must stop (a cell fell more than xdrop below the pre-group maximum).
-__device__ __forceinline__ bool filter_group(const uint32_t *__restrict__ mylut, uint32_t rb, uint32_t qb,
+// One 4-cell group.  y = ref byte << 16 | query byte (bytes 1 and 3 are junk): the group's 8 bits
+// of ref codes and 8 bits of query codes.  m1..m4 = dp4a selectors of the four prefixes in
+// processing order (ascending cells for the right walk, descending for the left walk).
+// Index arithmetic runs on the FMA pipe (dp2a: 16-bit fields x 8-bit multipliers) because the
+// integer ALU pipe is this kernel's bottleneck.  Returns true if the walk must stop (a cell fell
+// more than xdrop below the pre-group maximum).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+
+// lut_lane = shared-space byte address of this lane's LUT column (lut + lane*4); mul = 8 | 128<<8.
+__device__ __forceinline__ bool filter_group(uint32_t lut_lane, uint32_t mul, uint32_t y,
+                                             uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4,
                                              int &s, int &M, int X) {
-    const uint32_t ia = ((rb & 0x0Fu) << 4) | (qb & 0x0Fu);
-    const uint32_t ib = (rb & 0xF0u) | ((qb >> 4) & 0x0Fu);
-    const uint32_t sc = mylut[ia << 5] | (mylut[ib << 5] << 16);
-    const int p1 = __dp4a((int)sc, 0x00000001, s);
-    const int p2 = __dp4a((int)sc, 0x00000101, s);
-    const int p3 = __dp4a((int)sc, 0x00010101, s);
-    const int p4 = __dp4a((int)sc, 0x01010101, s);
+    const uint32_t oa = __dp2a_lo(y & 0x000F000Fu, mul, 0u) * 16u + lut_lane;   // (Rlo*16 + Qlo) * 128 + column
+    const uint32_t ob = __dp2a_lo(y & 0x00F000F0u, mul, lut_lane);              // (Rhi*16 + Qhi) * 128 + column
+    const uint32_t ea = lds_u32(oa);
+    const uint32_t eb = lds_u32(ob);
+    const int sc = (int)__byte_perm(ea, eb, 0x5410);                    // int8 scores of cells 0..3
+    const int p1 = __dp4a(sc, (int)m1, s);
+    const int p2 = __dp4a(sc, (int)m2, s);
+    const int p3 = __dp4a(sc, (int)m3, s);
+    const int p4 = __dp4a(sc, (int)m4, s);
     const int thr = M - X;
     const int mn = min(__vimin3_s32(p1, p2, p3), p4);
     M = __vimax3_s32(__vimax3_s32(p1, p2, p3), p4, M);
@@ -98,7 +116,8 @@ __device__ __forceinline__ bool filter_group(const uint32_t *__restrict__ mylut,
 
 __global__ void __launch_bounds__(FILTER_THREADS)
 k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              uint32_t num_hits, uint32_t *__restrict__ surv, uint32_t *__restrict__ counters) {
+              const uint32_t *__restrict__ plan, uint32_t hits_cap, uint32_t *__restrict__ surv,
+              uint32_t *__restrict__ counters) {
     extern __shared__ uint32_t lut[];
     __shared__ int diag[4];
     for (int i = threadIdx.x; i < FILTER_LUT_WORDS; i += blockDim.x) {
@@ -109,24 +128,33 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
 
+    const uint32_t num_hits = min(plan[1], hits_cap);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t *mylut = lut + lane;
+    // shared-space address of this lane's LUT column and the loop constants, pinned in registers
+    // (otherwise ptxas re-materialises them through the uniform datapath inside every group)
+    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + lane * 4u;
+    const uint32_t mul = P.k_mul, m4 = P.k_m4;
     const int X = P.xdrop;
 
     uint32_t cursor = 0, limit = 0;   // warp-uniform: the warp's current chunk of hit indices
     bool exhausted = false;           // warp-uniform: the global chunk counter ran past num_hits
-    bool active = false;
-    bool left = false;
+    // current hit of this lane
+    bool active = false, left = false;
     uint32_t h = 0, r0 = 0, q0 = 0, t = 0;
     int s = 0, M = 0, right_score = 0;
+    // next hit, loaded ahead of time so that its latency hides behind the current hit's tiles
+    bool have_next = false;
+    uint32_t nh = 0;
+    uint2 nhit = make_uint2(0, 0);
     unsigned long long ext_cells = 0;
 
     for (;;) {
-        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-        if (need) {
+        // ---- refill the prefetch slots from the warp cursor
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !have_next);
+        if (need && !(exhausted && cursor == limit)) {
             uint32_t avail = limit - cursor;
-            if (avail == 0 && !exhausted) {
+            if (avail == 0) {
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
                 c = __shfl_sync(0xFFFFFFFFu, c, 0);
@@ -137,15 +165,23 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
                 exhausted = avail == 0;
             }
             const uint32_t rank = __popc(need & lt_mask);
-            if (!active && rank < avail) {
-                h = cursor + rank;
-                const uint2 hit = __ldg(hits + h);
-                r0 = hit.x; q0 = hit.y;
-                active = true; left = false; t = 0; s = 0; M = 0;
+            if (!have_next && rank < avail) {
+                nh = cursor + rank;
+                nhit = __ldg(hits + nh);
+                have_next = true;
             }
             const uint32_t nneed = __popc(need);
             cursor += nneed < avail ? nneed : avail;
-            if (!__any_sync(0xFFFFFFFFu, active)) break;
+        }
+        // ---- idle lanes take their prefetched hit
+        if (!active && have_next) {
+            h = nh; r0 = nhit.x; q0 = nhit.y;
+            have_next = false;
+            active = true; left = false; t = 0; s = 0; M = 0;
+        }
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (exhausted) break;
+            continue;
         }
         if (active) {
             // window of this trip: right = cells r0+t .. r0+t+31 ; left = cells r0-t-32 .. r0-t-1
@@ -156,32 +192,37 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
             load_window(P.rrec, cr, R, Tr, Sr);
             load_window(P.qrec, cq, Q, Tq, Sq);
             uint32_t T = Tr | Tq, S = Sr | Sq;
-            if (left) { // processing order: cell k = t+1 first, i.e. window cell 31 first
-                R = reverse_fields(R); Q = reverse_fields(Q);
+            uint32_t rl = (uint32_t)R, rh = (uint32_t)(R >> 32), ql = (uint32_t)Q, qh = (uint32_t)(Q >> 32);
+            // dp4a prefix selectors in processing order
+            uint32_t m1 = 0x00000001u, m2 = 0x00000101u, m3 = 0x00010101u;
+            if (left) {
+                // processing order = descending cells: reverse the BYTES (groups) of the window;
+                // inside a group the descending order is taken by the selectors
+                const uint32_t a = __byte_perm(rh, 0, 0x0123), b = __byte_perm(rl, 0, 0x0123);
+                const uint32_t c = __byte_perm(qh, 0, 0x0123), d = __byte_perm(ql, 0, 0x0123);
+                rl = a; rh = b; ql = c; qh = d;
                 T = __brev(T); S = __brev(S);
+                m1 = 0x01000000u; m2 = 0x01010000u; m3 = 0x01010100u;
             }
             const int n_eff = __clz(__brev(T));          // cells before the first terminator (32 if none)
             const uint32_t valid = n_eff >= 32 ? 0xFFFFFFFFu : ((1u << n_eff) - 1u);
-            bool done = n_eff < 32;
-            bool survive = (S & valid) != 0;              // soft cell in range: let the exact kernel decide
-            if (!survive) {
-                if (n_eff == 32 && R == Q && P.diag_all_positive) {
-                    s += diag_sum32_f(R, diag);           // all-match tile: strictly increasing prefix
-                    M = max(M, s);
-                } else {
-                    int ng = (n_eff + 3) >> 2;            // groups to visit (the last may run past the terminator)
-                    const uint32_t rl = (uint32_t)R, rh = (uint32_t)(R >> 32);
-                    const uint32_t ql = (uint32_t)Q, qh = (uint32_t)(Q >> 32);
+            const bool survive = (S & valid) != 0;        // soft cell in range: let the exact kernel decide
+            int ng = survive ? 0 : (n_eff + 3) >> 2;      // groups to visit (the last may run past the terminator)
+            if (n_eff == 32 && !survive && rl == ql && rh == qh && P.diag_all_positive) {
+                s += diag_sum32_f(R, diag);               // all-match tile: strictly increasing prefix
+                M = max(M, s);
+                ng = 0;
+            }
 #pragma unroll
-                    for (int g = 0; g < 8; g++) {
-                        if (g < ng) {
-                            const uint32_t rw = g < 4 ? rl : rh, qw = g < 4 ? ql : qh;
-                            const uint32_t rb = (rw >> (8 * (g & 3))) & 0xFFu, qb = (qw >> (8 * (g & 3))) & 0xFFu;
-                            if (filter_group(mylut, rb, qb, s, M, X)) { ng = 0; done = true; }
-                        }
-                    }
+            for (int g = 0; g < 8; g++) {
+                if (g < ng) {
+                    // y = ref byte g << 16 | query byte g
+                    const uint32_t y = g < 4 ? __byte_perm(rl, ql, 0x0040 | (g & 3) << 8 | (4 + (g & 3)))
+                                             : __byte_perm(rh, qh, 0x0040 | (g & 3) << 8 | (4 + (g & 3)));
+                    if (filter_group(lut_lane, mul, y, m1, m2, m3, m4, s, M, X)) ng = -1;
                 }
             }
+            const bool done = ng < 0 || n_eff < 32;
             if (t >= 32u) ext_cells += 32;
             if (survive) {
                 surv[atomicAdd(counters + CTR_SURV, 1u)] = h;

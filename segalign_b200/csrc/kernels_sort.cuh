@@ -69,3 +69,78 @@ k_strip_tags(const Anchor *__restrict__ in, uint32_t n, sa_segment *__restrict__
 }
 
 } // namespace sa
+
+namespace sa {
+
+// ---------------------------------------------------------------------------------------------
+// One-launch finalisation for the common case of few anchors per call (a 250 kb chunk yields
+// ~10^2 HSPs): diagonal sort -> predecessor dedupe -> final order -> strip tags, all inside one
+// thread block on shared memory, with the element count read from device memory so the host
+// does not have to synchronise between the extension and the sort.  Same semantics as the
+// cub path above (src/seed_filter.cu:776-782); falls back to it by reporting
+// counters[CTR_OUT] = 0xFFFFFFFF when there are more than FINALIZE_CAP anchors.
+constexpr int FINALIZE_CAP = 1024; // 2 x 1024 x 20 B of static shared memory
+constexpr int FINALIZE_THREADS = 1024;
+
+template <typename Comp>
+__device__ __forceinline__ void block_bitonic_sort(Anchor *a, int n_pow2, Comp less) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    Anchor x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if (up ? less(y, x) : less(x, y)) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FINALIZE_THREADS)
+k_finalize_small(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_segment *__restrict__ out,
+                 uint32_t *__restrict__ counters) {
+    __shared__ Anchor a[FINALIZE_CAP];
+    __shared__ Anchor b[FINALIZE_CAP];
+    __shared__ uint32_t kept;
+    const uint32_t n = counters[0]; // CTR_ANCHORS
+    if (n > FINALIZE_CAP || n > anchor_cap) { // too many for one block (or the append overflowed): host takes the cub path
+        if (threadIdx.x == 0) counters[6] = 0xFFFFFFFFu;
+        return;
+    }
+    if (n == 0) {
+        if (threadIdx.x == 0) counters[6] = 0;
+        return;
+    }
+    int n2 = 1;
+    while (n2 < (int)n) n2 <<= 1;
+    Anchor pad; // sorts after every real anchor under both orders
+    pad.tag = 0xFFFFFFFFu; pad.ref_start = 0xFFFFFFFFu; pad.query_start = 0; pad.len = 0xFFFFFFFFu; pad.score = 0;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) a[i] = i < (int)n ? anchors[i] : pad;
+    if (threadIdx.x == 0) kept = 0;
+    __syncthreads();
+    block_bitonic_sort(a, n2, CompDiag());
+    // unique_copy head flags against the predecessor of the SORTED INPUT; survivors go to b[] in
+    // any order (the final order is total)
+    for (int i = threadIdx.x; i < (int)n; i += blockDim.x) {
+        bool keep = i == 0 || a[i - 1].tag != a[i].tag || !hsp_equal(a[i - 1], a[i]);
+        if (keep) b[atomicAdd(&kept, 1u)] = a[i];
+    }
+    __syncthreads();
+    const uint32_t m = kept;
+    int m2 = 1;
+    while (m2 < (int)m) m2 <<= 1;
+    for (int i = (int)m + threadIdx.x; i < m2; i += blockDim.x) b[i] = pad;
+    __syncthreads();
+    block_bitonic_sort(b, m2, CompLastz());
+    for (int i = threadIdx.x; i < (int)m; i += blockDim.x) {
+        sa_segment s;
+        s.ref_start = b[i].ref_start; s.query_start = b[i].query_start; s.len = b[i].len; s.score = b[i].score;
+        out[i] = s;
+    }
+    if (threadIdx.x == 0) counters[6] = m;
+}
+
+} // namespace sa

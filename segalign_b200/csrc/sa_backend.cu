@@ -100,6 +100,7 @@ struct Workspace {
     uint32_t *d_flags = nullptr; size_t flags_cap = 0;
     uint32_t *d_excl = nullptr; size_t excl_cap = 0;
     uint32_t *h_small = nullptr; // pinned, 16 words
+    sa_segment *h_out = nullptr; // pinned staging for the first FINALIZE_CAP result records
 };
 
 struct GpuCtx {
@@ -243,6 +244,8 @@ int make_workspace(int gpu_index, Workspace *&out) {
     CU(cudaMalloc((void **)&w->d_plan, 4 * sizeof(uint32_t)), SA_ERR_MALLOC);
     CU(cudaMalloc((void **)&w->d_counters, 8 * sizeof(uint32_t)), SA_ERR_MALLOC);
     CU(cudaMallocHost((void **)&w->h_small, 16 * sizeof(uint32_t)), SA_ERR_MALLOC);
+    CU(cudaMallocHost((void **)&w->h_out, FINALIZE_CAP * sizeof(sa_segment)), SA_ERR_MALLOC);
+    TRY(ensure(w->d_out, w->out_cap, FINALIZE_CAP, "hsp_out", 1, 1));
     TRY(ensure(w->d_seeds, w->seeds_cap, std::max<size_t>(G.max_seeds, 1024), "seed_offsets", 1, 1));
     TRY(ensure(w->d_prefix, w->prefix_cap, std::max<size_t>(G.max_seeds, 1024), "hit_num", 1, 1));
     TRY(ensure(w->d_limit_pos, w->limit_cap, 64, "limit_pos", 1, 1));
@@ -257,6 +260,7 @@ void destroy_workspace(Workspace *w) {
     cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
+    cudaFreeHost(w->h_out);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
     delete w;
@@ -298,6 +302,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
     cudaStream_t st = w->stream;
     uint64_t launches = 0;
     uint32_t num_hits = 0, num_iter = 0, n_pre = 0, n_final = 0, n_surv = 0;
+    sa_segment *result = nullptr;
     unsigned long long ext_cells = 0;
 
     // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
@@ -346,58 +351,80 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
             FilterParams F;
             F.rrec = g.ref.rec; F.qrec = q.rec;
             F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
+            F.k_mul = 8u | (128u << 8); F.k_m4 = 0x01010101u;
             k_filter_hits<<<G.filter_grid, FILTER_THREADS, FILTER_LUT_WORDS * sizeof(uint32_t), st>>>(
-                F, g.d_sub_mat, w->d_hits, num_hits, w->d_surv, w->d_counters);
+                F, g.d_sub_mat, w->d_hits, w->d_plan, (uint32_t)std::min<size_t>(w->hits_cap, 0xFFFFFFFFu), w->d_surv, w->d_counters);
             launches++;
             pt.mark(PH_FILTER);
         }
+        bool staged = false; // result records already in w->h_out
         for (;;) {
             // stage B: exact extension (of the survivors, or of every hit without the filter)
-            k_extend_hits<<<grid_for(filter ? std::max<uint32_t>(num_hits / 64, 4096) : num_hits, 128, 16), 128, 0, st>>>(
-                P, g.d_sub_mat, w->d_hits, 0u, num_hits, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
+            // (two lanes per work item; with the filter the item count is only known on the device)
+            k_extend_hits<<<grid_for(filter ? std::max<size_t>(num_hits / 32, 8192) : 2 * (size_t)num_hits, 128, 16), 128, 0, st>>>(
+                P, g.d_sub_mat, w->d_hits, num_hits, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
                 w->d_anchors_a, (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu), w->d_counters);
-            launches++;
+            pt.mark(PH_EXTEND);
+            // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the
+            //    anchors fit, with the count read on the device; the first FINALIZE_CAP records and
+            //    the counters come back in the same synchronisation
+            k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu),
+                                                             w->d_out, w->d_counters);
+            pt.mark(PH_SORT);
+            launches += 2;
             CU(cudaMemcpyAsync(w->h_small, w->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+            CU(cudaMemcpyAsync(w->h_out, w->d_out, FINALIZE_CAP * sizeof(sa_segment), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
             CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-            n_pre = w->h_small[0];
-            n_surv = filter ? w->h_small[4] : num_hits;
-            memcpy(&ext_cells, &w->h_small[2], 8);
+            n_pre = w->h_small[CTR_ANCHORS];
+            n_surv = filter ? w->h_small[CTR_SURV] : num_hits;
+            memcpy(&ext_cells, &w->h_small[CTR_EXT_LO], 8);
             if (n_pre <= w->anchors_a_cap) break;
             TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced")); // rare: rerun stage B
             CU(cudaMemsetAsync(w->d_counters, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
         }
-        pt.mark(PH_EXTEND);
-        // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782)
-        if (n_pre > 0) {
+        if (w->h_small[CTR_OUT] != 0xFFFFFFFFu) {
+            n_final = w->h_small[CTR_OUT];
+            staged = true;
+        } else {
+            // many anchors (self-alignment, repeat families): device-wide sorts
             TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
             TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
-            k_dedupe<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + 1);
-            CU(cudaMemcpyAsync(w->h_small, w->d_counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+            CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+            k_dedupe<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + CTR_DEDUPE);
+            CU(cudaMemcpyAsync(w->h_small, w->d_counters + CTR_DEDUPE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
             CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
             n_final = w->h_small[0];
             TRY(sort_anchors(w, w->d_anchors_b, n_final, true));
             TRY(ensure(w->d_out, w->out_cap, n_final, "hsp_out"));
             k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_b, n_final, w->d_out);
             launches += 8;
+            pt.mark(PH_SORT);
         }
-        pt.mark(PH_SORT);
+        // 6. result (seed_filter.cu:786-788, :804-822)
+        sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
+        if (!res) return fail(SA_ERR_MALLOC, "malloc of result failed");
+        if (staged) {
+            memcpy(res + 1, w->h_out, (size_t)n_final * sizeof(sa_segment));
+        } else if (n_final > 0) {
+            cudaError_t e = cudaMemcpyAsync(res + 1, w->d_out, (size_t)n_final * sizeof(sa_segment), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                free(res);
+                return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for hsp_output failed with error \" %s \"",
+                            (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
+            }
+        }
+        result = res;
     }
-    // 6. result (seed_filter.cu:786-788, :804-822)
-    sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
-    if (!res) return fail(SA_ERR_MALLOC, "malloc of result failed");
+    if (!result) { // no hits at all: header only
+        result = (sa_segment *)malloc(sizeof(sa_segment));
+        if (!result) return fail(SA_ERR_MALLOC, "malloc of result failed");
+    }
+    sa_segment *res = result;
     res[0].ref_start = 0;
     res[0].query_start = 0;
     res[0].len = n_final;
     res[0].score = (int32_t)num_hits;
-    if (n_final > 0) {
-        cudaError_t e = cudaMemcpyAsync(res + 1, w->d_out, (size_t)n_final * sizeof(sa_segment), cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            free(res);
-            return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for hsp_output failed with error \" %s \"",
-                        (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
-        }
-    }
     pt.mark(PH_D2H);
     if (pt.on) CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
     CU(cudaGetLastError(), SA_ERR_KERNEL);

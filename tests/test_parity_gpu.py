@@ -21,6 +21,29 @@ def test_backend_matches_reference_golden(backend, case):
 
 
 @pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+def test_exact_stage_alone_matches_reference_golden(backend, case, monkeypatch):
+    """SEGALIGN_B200_FILTER=0 sends every hit to the exact kernel (stage B): it must reproduce the
+    reference on its own, so that the filter (stage A) can only ever remove non-HSPs."""
+    monkeypatch.setenv("SEGALIGN_B200_FILTER", "0")
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case)
+    H.assert_calls_equal(got, want, "exact stage alone vs reference golden")
+
+
+def test_filter_keeps_a_small_superset(backend):
+    """The filter's survivors are few (it is the point of the stage) and contain every HSP."""
+    case = H.CASES_BY_NAME["masked_multichrom"]
+    ref, query = case.inputs()
+    backend.reset_stats()
+    got = H.run_backend(backend, case, ref, query)
+    st = backend.stats()
+    assert st["hits"] > 100_000
+    # this small, closely related pair has ~23 % true (homologous) hits; random hits must be gone
+    assert st["anchors_pre_dedupe"] <= st["survivors"] < 0.3 * st["hits"]
+    assert sum(g[4].size - 1 for g in got) == st["hsps"]
+
+
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
 def test_device_seeding_matches_reference_golden(backend, case):
     """sa_seed_and_filter_range (seed words generated on the GPU) returns exactly what
     the reference returns for the host-built seed vector of the same chunk."""
