@@ -21,8 +21,9 @@ Numbers on the JSON line:
             query block is uploaded (sa_send_query), every unit's seed vector is built on the
             host (sa_host_chunk_seeds == src/seeder.cpp:57-74) and handed to
             sa_seed_and_filter (== g_SeedAndFilter), HSPs come back to host memory.
-  roofline  k_extend_hits (the dominant kernel): algorithmic bytes 64*H + E (SURVEY 8d B_X) per
-            launch / CUDA-event duration of that kernel on its own stream, vs MEASURED_PEAKS hbm.
+  roofline  k_filter_hits (the dominant kernel: the extension's score filter over ALL hits):
+            algorithmic bytes 64*H + E (SURVEY 8d B_X) per launch / CUDA-event duration of that
+            kernel on its own stream inside the timed region, vs MEASURED_PEAKS hbm.
   cpu_baseline  LASTZ (oracle/_ref/lastz, built from the reference's submodule) on a bounded
             sample of the same workload, one process per host core.
 """
@@ -270,13 +271,13 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     n_launch = max(1, st_res["calls"])
     alg_bytes = 64.0 * st_res["hits"] + st_res["ext_cells"]
-    t_ext = st_res["ms_extend"] * 1e-3
+    t_ext = st_res["ms_prefilter"] * 1e-3
     achieved = alg_bytes / t_ext / 1e9 if t_ext > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_extend_hits", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_filter_hits", "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                 "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
-                "avg_launch_ms": round(st_res["ms_extend"] / n_launch, 4), "launches": n_launch,
+                "avg_launch_ms": round(st_res["ms_prefilter"] / n_launch, 4), "launches": n_launch,
                 "traffic": None,
                 "lookup": {"kernel": "k_count_hits+scan+k_expand_hits",
                            "algorithmic_bytes_per_launch": round((16.0 * st_res["seeds"] + 4.0 * st_res["hits"]) / n_launch),

@@ -145,10 +145,11 @@ k_seed_flags(const uint32_t *__restrict__ m1, int span, uint32_t j0, uint32_t j1
 __global__ void __launch_bounds__(256)
 k_seed_emit(const uint64_t *__restrict__ p2, const uint32_t *__restrict__ flags,
             const uint32_t *__restrict__ excl, ShapeDesc sh, int transition, uint32_t j0,
-            uint32_t j1, uint64_t *__restrict__ seeds) {
+            uint32_t j1, uint64_t *__restrict__ seeds, uint32_t *__restrict__ d_num_seeds) {
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t per = 1u + (transition ? (uint32_t)sh.num_trans : 0u);
     for (uint32_t j = j0 + blockIdx.x * blockDim.x + threadIdx.x; j < j1; j += stride) {
+        if (j == j1 - 1) *d_num_seeds = (excl[j - j0] + flags[j - j0]) * per; // total seed words
         if (!flags[j - j0]) continue;
         uint64_t kmer = kmer_from_window(load_p2_window(p2, j), sh);
         uint64_t *o = seeds + (size_t)excl[j - j0] * per;

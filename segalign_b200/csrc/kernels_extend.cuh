@@ -104,6 +104,47 @@ __device__ __forceinline__ DirResult extend_dir(const ExtendParams &P, const int
                 // strictly increasing prefix: no x-drop possible, the best moves to the last cell
                 s += diag_sum32(rw, diag);
                 if (s > M) { M = s; mp = base + 31; }
+            } else if (P.scores_fit_int8) {
+                // 4-cell groups: all table lookups first (they do not depend on the running score),
+                // then per group four dp4a prefix sums; the group is walked cell by cell only when
+                // an x-drop inside it cannot be excluded.  Same result as the sequential rule.
+                uint32_t sc[8];
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const uint32_t rb = (uint32_t)(rw >> (8 * g)) & 0xFFu, qb = (uint32_t)(qw >> (8 * g)) & 0xFFu;
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t idx = ((rb >> (2 * c)) & 3u) << 2 | ((qb >> (2 * c)) & 3u);
+                        v |= ((uint32_t)lut16[idx] & 0xFFu) << (8 * c);
+                    }
+                    sc[g] = v;
+                }
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    if (stop) break;
+                    const int p1 = __dp4a((int)sc[g], 0x00000001, s), p2 = __dp4a((int)sc[g], 0x00000101, s);
+                    const int p3 = __dp4a((int)sc[g], 0x00010101, s), p4 = __dp4a((int)sc[g], 0x01010101, s);
+                    const int mx = max(__vimax3_s32(p1, p2, p3), p4);
+                    const int mn = min(__vimin3_s32(p1, p2, p3), p4);
+                    if (max(M, mx) - mn <= X) { // no cell of the group can be > xdrop below the running max
+                        if (mx > M) {
+                            M = mx;
+                            mp = base + 4 * g + (p1 == mx ? 0 : (p2 == mx ? 1 : (p3 == mx ? 2 : 3)));
+                        }
+                        s = p4;
+                    } else {
+                        const int pj[4] = {p1, p2, p3, p4};
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            if (!stop) {
+                                s = pj[c];
+                                if (s > M) { M = s; mp = base + 4 * g + c; }
+                                if (M - s > X) stop = true;
+                            }
+                        }
+                    }
+                }
             } else {
 #pragma unroll 8
                 for (int j = 0; j < 32; j++) {
@@ -213,20 +254,52 @@ __device__ __forceinline__ uint32_t iteration_of(const uint32_t *__restrict__ hi
 // count read from counters[4] on the device so the host need not synchronise in between);
 // otherwise it walks hits [0, h_end) directly.  Lanes 2i / 2i+1 of a warp extend work item i to
 // the right / to the left.
-__global__ void __launch_bounds__(128)
+// Exact-duplicate suppression at append time.  Every seed hit inside one homologous run extends
+// to the same HSP, so ~99 % of the passing records of a call are byte-identical copies.  Removing
+// identical records (same iteration tag) before the diagonal sort cannot change the reference's
+// sort -> unique_copy -> sort result: copies sort next to each other and unique_copy keeps the
+// first of them, compared against the same predecessor.  Open addressing; a full
+// or contended table only means "not suppressed" -- never a dropped record.
+struct DedupTable {
+    unsigned long long *k0; // ref_start | query_start << 32   (all-ones = empty)
+    unsigned long long *k1; // len | score << 32               (all-ones = empty)
+    uint32_t *tagbits;      // bit t: the record was already appended under iteration tag t
+    uint32_t mask;          // slots - 1 (power of two); 0 disables the table
+};
+
+__device__ __forceinline__ bool dedup_is_new(const DedupTable &T, const sa_segment &seg, uint32_t tag) {
+    if (T.mask == 0 || tag >= 32u) return true;
+    const unsigned long long my0 = (unsigned long long)seg.ref_start | ((unsigned long long)seg.query_start << 32);
+    const unsigned long long my1 = (unsigned long long)seg.len | ((unsigned long long)(uint32_t)seg.score << 32);
+    if (my0 == ~0ull || my1 == ~0ull) return true;
+    uint32_t i = (uint32_t)((my0 * 0x9E3779B97F4A7C15ull) >> 40) ^ (uint32_t)(my1 * 0x85EBCA6Bu);
+    for (int probe = 0; probe < 64; probe++, i++) {
+        i &= T.mask;
+        const unsigned long long o0 = atomicCAS(T.k0 + i, ~0ull, my0);
+        if (o0 != ~0ull && o0 != my0) continue;
+        const unsigned long long o1 = atomicCAS(T.k1 + i, ~0ull, my1);
+        if (o1 != ~0ull && o1 != my1) continue; // same start pair, other length/score: next slot
+        return ((atomicOr(T.tagbits + i, 1u << tag) >> tag) & 1u) == 0;
+    }
+    return true;
+}
+
+constexpr int EXTEND_THREADS = 32; // one warp per block: fits beside the resident filter blocks
+
+__global__ void __launch_bounds__(EXTEND_THREADS)
 k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
               uint32_t h_end, const uint32_t *__restrict__ surv,
               const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors,
-              uint32_t anchor_cap, uint32_t *__restrict__ counters) {
+              uint32_t anchor_cap, uint32_t *__restrict__ counters, DedupTable dedup) {
     __shared__ int sub[64];
     __shared__ int lut16[16];
     __shared__ int diag[4];
-    if (threadIdx.x < 64) sub[threadIdx.x] = sub_mat[threadIdx.x];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) sub[i] = sub_mat[i];
     if (threadIdx.x < 16) lut16[threadIdx.x] = sub_mat[(threadIdx.x >> 2) * 8 + (threadIdx.x & 3)];
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
-    if (surv) h_end = counters[4];
+    h_end = surv ? counters[4] : min(plan[1], h_end); // counts known only on the device
     const uint32_t items_per_pass = (gridDim.x * blockDim.x) >> 1;
     const bool left = threadIdx.x & 1u;
     unsigned long long cells = 0;
@@ -255,11 +328,13 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
         for (int c = 0; c < 4; c++) cnt[c] = C.cnt[c] + __shfl_down_sync(0xFFFFFFFFu, C.cnt[c], 1);
         if (valid && !left) {
             sa_segment seg;
-            if (finish_hit(P, hit.x, hit.y, D, L, cnt, &seg)) {
+            uint32_t tag = 0;
+            if (finish_hit(P, hit.x, hit.y, D, L, cnt, &seg) &&
+                dedup_is_new(dedup, seg, tag = iteration_of(hit_bound, plan[0], h))) {
                 uint32_t slot = atomicAdd(counters, 1u);
                 if (slot < anchor_cap) {
                     Anchor a;
-                    a.tag = iteration_of(hit_bound, plan[0], h);
+                    a.tag = tag;
                     a.ref_start = seg.ref_start;
                     a.query_start = seg.query_start;
                     a.len = seg.len;

@@ -35,8 +35,8 @@
 namespace sa {
 
 constexpr int FILTER_THREADS = 256;
-constexpr int FILTER_LUT_WORDS = 256 * 32;          // 32 KB: entry idx for lane l at [idx*32 + l]
-constexpr uint32_t FILTER_CHUNK = 2048;             // hits per warp-level work grab
+constexpr int FILTER_LUT_WORDS = 256 * 16;          // 16 KB: entry idx for lane l at [idx*16 + (l & 15)]: at most 2-way bank conflicts
+constexpr uint32_t FILTER_CHUNK = 128;              // hits per warp-level work grab (staged in shared memory)
 
 struct FilterParams {
     const uint4 *rrec;   // reference records, index 0 = first 32 bases (front/back padded)
@@ -46,7 +46,7 @@ struct FilterParams {
     int diag_all_positive;
     // loop constants handed over as kernel parameters so that they are read from the constant
     // bank as instruction operands (as immediates ptxas re-materialises them in every group)
-    uint32_t k_mul; // 8 | 128 << 8 : dp2a multipliers
+    uint32_t k_mul; // 4 | 64 << 8 : dp2a multipliers (16-bit fields -> LUT byte offsets)
     uint32_t k_m4;  // 0x01010101   : dp4a selector of the full group
 };
 
@@ -94,34 +94,24 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
     return v;
 }
 
-// lut_lane = shared-space byte address of this lane's LUT column (lut + lane*4); mul = 8 | 128<<8.
-__device__ __forceinline__ bool filter_group(uint32_t lut_lane, uint32_t mul, uint32_t y,
-                                             uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4,
-                                             int &s, int &M, int X) {
-    const uint32_t oa = __dp2a_lo(y & 0x000F000Fu, mul, 0u) * 16u + lut_lane;   // (Rlo*16 + Qlo) * 128 + column
-    const uint32_t ob = __dp2a_lo(y & 0x00F000F0u, mul, lut_lane);              // (Rhi*16 + Qhi) * 128 + column
-    const uint32_t ea = lds_u32(oa);
-    const uint32_t eb = lds_u32(ob);
-    const int sc = (int)__byte_perm(ea, eb, 0x5410);                    // int8 scores of cells 0..3
-    const int p1 = __dp4a(sc, (int)m1, s);
-    const int p2 = __dp4a(sc, (int)m2, s);
-    const int p3 = __dp4a(sc, (int)m3, s);
-    const int p4 = __dp4a(sc, (int)m4, s);
-    const int thr = M - X;
-    const int mn = min(__vimin3_s32(p1, p2, p3), p4);
-    M = __vimax3_s32(__vimax3_s32(p1, p2, p3), p4, M);
-    s = p4;
-    return mn < thr;
+// Scores of one 4-cell group as four int8.  lut_lane = shared-space byte address of this lane's
+// LUT column (lut + (lane & 15)*4); mul = 4 | 64<<8; y = ref byte << 16 | query byte (bytes 1, 3 junk).
+// Index arithmetic runs on the FMA pipe (dp2a: 16-bit fields x 8-bit multipliers) because the
+// integer ALU pipe is this kernel's busiest.
+__device__ __forceinline__ uint32_t group_scores(uint32_t lut_lane, uint32_t mul, uint32_t y) {
+    const uint32_t oa = __dp2a_lo(y & 0x000F000Fu, mul, 0u) * 16u + lut_lane;   // (Rlo*16 + Qlo) * 64 + column
+    const uint32_t ob = __dp2a_lo(y & 0x00F000F0u, mul, lut_lane);              // (Rhi*16 + Qhi) * 64 + column
+    return __byte_perm(lds_u32(oa), lds_u32(ob), 0x5410);
 }
 
-__global__ void __launch_bounds__(FILTER_THREADS)
+__global__ void __launch_bounds__(FILTER_THREADS, 6)
 k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
               const uint32_t *__restrict__ plan, uint32_t hits_cap, uint32_t *__restrict__ surv,
               uint32_t *__restrict__ counters) {
     extern __shared__ uint32_t lut[];
     __shared__ int diag[4];
     for (int i = threadIdx.x; i < FILTER_LUT_WORDS; i += blockDim.x) {
-        const int idx = i >> 5, rn = idx >> 4, qn = idx & 15;
+        const int idx = i >> 4, rn = idx >> 4, qn = idx & 15;
         const int s0 = sub_mat[(rn & 3) * 8 + (qn & 3)], s1 = sub_mat[(rn >> 2) * 8 + (qn >> 2)];
         lut[i] = (uint32_t)(uint8_t)(int8_t)s0 | ((uint32_t)(uint8_t)(int8_t)s1 << 8);
     }
@@ -133,51 +123,53 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
     const uint32_t lt_mask = (1u << lane) - 1u;
     // shared-space address of this lane's LUT column and the loop constants, pinned in registers
     // (otherwise ptxas re-materialises them through the uniform datapath inside every group)
-    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + lane * 4u;
+    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + (lane & 15u) * 4u;
     const uint32_t mul = P.k_mul, m4 = P.k_m4;
     const int X = P.xdrop;
 
-    uint32_t cursor = 0, limit = 0;   // warp-uniform: the warp's current chunk of hit indices
-    bool exhausted = false;           // warp-uniform: the global chunk counter ran past num_hits
+    // Work distribution: a warp grabs FILTER_CHUNK consecutive hits at a time from a global
+    // counter (fine-grained, so that all warps finish together) and stages them in shared memory
+    // with one coalesced load; lanes then pick hits from the staged chunk as they become free.
+    __shared__ uint2 hitbuf[FILTER_THREADS / 32][FILTER_CHUNK];
+    uint2 *mybuf = hitbuf[threadIdx.x >> 5];
+    uint32_t chunk_start = 0, cursor = 0, limit = 0; // warp-uniform: current chunk [chunk_start, limit), next unassigned hit
+    bool exhausted = false;                          // warp-uniform: the global chunk counter ran past num_hits
     // current hit of this lane
     bool active = false, left = false;
     uint32_t h = 0, r0 = 0, q0 = 0, t = 0;
     int s = 0, M = 0, right_score = 0;
-    // next hit, loaded ahead of time so that its latency hides behind the current hit's tiles
-    bool have_next = false;
-    uint32_t nh = 0;
-    uint2 nhit = make_uint2(0, 0);
     unsigned long long ext_cells = 0;
 
     for (;;) {
-        // ---- refill the prefetch slots from the warp cursor
-        const unsigned need = __ballot_sync(0xFFFFFFFFu, !have_next);
-        if (need && !(exhausted && cursor == limit)) {
-            uint32_t avail = limit - cursor;
-            if (avail == 0) {
+        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+        if (need && !exhausted) {
+            if (cursor == limit) { // chunk used up: grab and stage the next one
                 uint32_t c = 0;
                 if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
                 c = __shfl_sync(0xFFFFFFFFu, c, 0);
                 const unsigned long long start = (unsigned long long)c * FILTER_CHUNK;
-                cursor = start < num_hits ? (uint32_t)start : num_hits;
-                limit = (num_hits - cursor < FILTER_CHUNK) ? num_hits : cursor + FILTER_CHUNK;
-                avail = limit - cursor;
-                exhausted = avail == 0;
+                chunk_start = start < num_hits ? (uint32_t)start : num_hits;
+                limit = (num_hits - chunk_start < FILTER_CHUNK) ? num_hits : chunk_start + FILTER_CHUNK;
+                cursor = chunk_start;
+                exhausted = cursor == limit;
+                __syncwarp();
+#pragma unroll
+                for (uint32_t k = 0; k < FILTER_CHUNK / 32; k++) {
+                    const uint32_t i = chunk_start + k * 32u + lane;
+                    if (i < limit) mybuf[k * 32u + lane] = __ldg(hits + i);
+                }
+                __syncwarp();
             }
+            const uint32_t avail = limit - cursor;
             const uint32_t rank = __popc(need & lt_mask);
-            if (!have_next && rank < avail) {
-                nh = cursor + rank;
-                nhit = __ldg(hits + nh);
-                have_next = true;
+            if (!active && rank < avail) {
+                h = cursor + rank;
+                const uint2 hit = mybuf[h - chunk_start];
+                r0 = hit.x; q0 = hit.y;
+                active = true; left = false; t = 0; s = 0; M = 0;
             }
             const uint32_t nneed = __popc(need);
             cursor += nneed < avail ? nneed : avail;
-        }
-        // ---- idle lanes take their prefetched hit
-        if (!active && have_next) {
-            h = nh; r0 = nhit.x; q0 = nhit.y;
-            have_next = false;
-            active = true; left = false; t = 0; s = 0; M = 0;
         }
         if (!__any_sync(0xFFFFFFFFu, active)) {
             if (exhausted) break;
@@ -207,22 +199,38 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
             const int n_eff = __clz(__brev(T));          // cells before the first terminator (32 if none)
             const uint32_t valid = n_eff >= 32 ? 0xFFFFFFFFu : ((1u << n_eff) - 1u);
             const bool survive = (S & valid) != 0;        // soft cell in range: let the exact kernel decide
-            int ng = survive ? 0 : (n_eff + 3) >> 2;      // groups to visit (the last may run past the terminator)
+            // ---- the tile body is straight-line code: first all table lookups of the tile (independent
+            // of the running score, so their latencies overlap), then the short dependent chain.
+            // Groups at or past the one holding the first terminator are neutralised (score 0).
+            const int ng = survive ? 0 : (n_eff + 3) >> 2; // groups to visit (the last may run past the terminator)
+            bool dropped = false;
             if (n_eff == 32 && !survive && rl == ql && rh == qh && P.diag_all_positive) {
                 s += diag_sum32_f(R, diag);               // all-match tile: strictly increasing prefix
                 M = max(M, s);
-                ng = 0;
-            }
+            } else {
+                uint32_t sc[8];
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
-                if (g < ng) {
-                    // y = ref byte g << 16 | query byte g
+                for (int g = 0; g < 8; g++) {
                     const uint32_t y = g < 4 ? __byte_perm(rl, ql, 0x0040 | (g & 3) << 8 | (4 + (g & 3)))
                                              : __byte_perm(rh, qh, 0x0040 | (g & 3) << 8 | (4 + (g & 3)));
-                    if (filter_group(lut_lane, mul, y, m1, m2, m3, m4, s, M, X)) ng = -1;
+                    const uint32_t v = group_scores(lut_lane, mul, y);
+                    sc[g] = g < ng ? v : 0u;
+                }
+#pragma unroll
+                for (int g = 0; g < 8; g++) {
+                    const int p1 = __dp4a((int)sc[g], (int)m1, s);
+                    const int p2 = __dp4a((int)sc[g], (int)m2, s);
+                    const int p3 = __dp4a((int)sc[g], (int)m3, s);
+                    const int p4 = __dp4a((int)sc[g], (int)m4, s);
+                    const int mn = min(__vimin3_s32(p1, p2, p3), p4);
+                    // a cell more than xdrop below a maximum reached BEFORE this group: the reference's
+                    // walk has stopped by here.  Later groups of the tile still raise M (over-estimate).
+                    dropped |= mn < M - X;
+                    M = __vimax3_s32(__vimax3_s32(p1, p2, p3), p4, M);
+                    s = p4;
                 }
             }
-            const bool done = ng < 0 || n_eff < 32;
+            const bool done = dropped || n_eff < 32;
             if (t >= 32u) ext_cells += 32;
             if (survive) {
                 surv[atomicAdd(counters + CTR_SURV, 1u)] = h;

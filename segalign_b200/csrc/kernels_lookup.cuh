@@ -10,14 +10,20 @@
 namespace sa {
 
 // bucket size per seed word: n = T[k] - (k ? T[k-1] : 0)   (seed_filter.cu:172-180)
+// The seed count lives in device memory (*d_num_seeds): with device-side seeding the host only
+// knows an upper bound (max_items) when it enqueues the call.  Slots past the count get 0 hits.
 __global__ void __launch_bounds__(256)
-k_count_hits(const uint64_t *__restrict__ seeds, uint32_t num_seeds,
+k_count_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint32_t *__restrict__ d_num_seeds,
              const uint32_t *__restrict__ index_table, uint32_t *__restrict__ counts) {
+    const uint32_t num_seeds = min(*d_num_seeds, max_items);
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < num_seeds; s += stride) {
-        uint32_t kmer = (uint32_t)(seeds[s] >> 32);
-        uint32_t n = __ldg(index_table + kmer);
-        if (kmer > 0) n -= __ldg(index_table + kmer - 1);
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < max_items; s += stride) {
+        uint32_t n = 0;
+        if (s < num_seeds) {
+            uint32_t kmer = (uint32_t)(seeds[s] >> 32);
+            n = __ldg(index_table + kmer);
+            if (kmer > 0) n -= __ldg(index_table + kmer - 1);
+        }
         counts[s] = n;
     }
 }
@@ -36,10 +42,13 @@ __device__ __forceinline__ uint32_t lower_bound_dev(const uint32_t *a, uint32_t 
 // hit_bound[i] = flat hit index one past iteration i.
 // Reference UB zone (SURVEY A.11 i): lower_bound == 0 -> pos wraps; defined here as an empty
 // iteration (limit_pos = 0xFFFFFFFF, bound 0), same as oracle/sa_oracle.c.
-__global__ void k_plan_iterations(const uint32_t *__restrict__ prefix, uint32_t num_seeds,
+// plan[2] = number of seed words (input, written by the seeding step).
+__global__ void k_plan_iterations(const uint32_t *__restrict__ prefix, uint32_t max_items,
                                   uint32_t max_hits, uint32_t cap, uint32_t *__restrict__ limit_pos,
                                   uint32_t *__restrict__ hit_bound, uint32_t *__restrict__ plan) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const uint32_t num_seeds = min(plan[2], max_items);
+    if (num_seeds == 0) { plan[0] = 0; plan[1] = 0; return; }
     uint32_t num_hits = prefix[num_seeds - 1];
     plan[1] = num_hits;
     if (num_hits == 0) { plan[0] = 0; return; }
@@ -65,9 +74,11 @@ __global__ void k_plan_iterations(const uint32_t *__restrict__ prefix, uint32_t 
 // (seed_filter.cu:204,220); flat order is seed-major, i.e. the hits of seed s occupy
 // [prefix[s] - n_s, prefix[s]).  The order inside a bucket is irrelevant.
 __global__ void __launch_bounds__(256)
-k_expand_hits(const uint64_t *__restrict__ seeds, uint32_t num_seeds,
+k_expand_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint32_t *__restrict__ d_num_seeds,
               const uint32_t *__restrict__ index_table, const uint32_t *__restrict__ pos_table,
-              const uint32_t *__restrict__ prefix, uint32_t seed_size, uint2 *__restrict__ hits) {
+              const uint32_t *__restrict__ prefix, uint32_t seed_size, uint2 *__restrict__ hits,
+              uint32_t hits_cap) {
+    const uint32_t num_seeds = min(*d_num_seeds, max_items);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -107,7 +118,9 @@ k_expand_hits(const uint64_t *__restrict__ seeds, uint32_t num_seeds,
             uint32_t o_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
             uint32_t o_start = __shfl_sync(0xFFFFFFFFu, start, lo);
             uint32_t o_q = __shfl_sync(0xFFFFFFFFu, q, lo);
-            if (f < total) {
+            // hits past the buffer capacity are dropped here; the host sees num_hits > capacity at
+            // its single synchronisation point, grows the buffers and replays the call
+            if (f < total && gbase + f < hits_cap) {
                 uint32_t r = __ldg(pos_table + o_start + (f - o_excl)) + seed_size;
                 hits[(size_t)gbase + f] = make_uint2(r, o_q);
             }

@@ -81,6 +81,8 @@ int ensure(T *&ptr, size_t &cap, size_t need, const char *tag, size_t slack_num 
     return SA_OK;
 }
 
+constexpr uint32_t kDedupSlots = 1u << 16; // exact-duplicate table of the exact stage (kernels_extend.cuh)
+
 struct Workspace {
     int gpu = 0; // index into G.gpus
     cudaStream_t stream = nullptr;
@@ -93,6 +95,7 @@ struct Workspace {
     uint32_t *d_counters = nullptr;  // [0]=anchor cursor [1]=dedupe cursor [2..3]=ext cells
     uint2 *d_hits = nullptr; size_t hits_cap = 0;
     uint32_t *d_surv = nullptr; size_t surv_cap = 0; // filter survivors (hit indices)
+    unsigned long long *d_dedup = nullptr;           // exact-duplicate table: k0[slots], k1[slots], tagbits[slots]
     Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
     Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
     sa_segment *d_out = nullptr; size_t out_cap = 0;
@@ -125,7 +128,9 @@ struct Global {
     uint32_t term_codes = 0;   // non-ACGT codes that always trip the X-drop rule (kernels_filter.cuh)
     bool filter_ok = false;    // ACGT x ACGT scores fit int8: the filter stage is usable
     bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
+    bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
     int filter_grid = 0;
+    int extend_grid = 0;
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
     uint32_t query_len[SA_BUFFER_DEPTH] = {};
@@ -246,6 +251,7 @@ int make_workspace(int gpu_index, Workspace *&out) {
     CU(cudaMallocHost((void **)&w->h_small, 16 * sizeof(uint32_t)), SA_ERR_MALLOC);
     CU(cudaMallocHost((void **)&w->h_out, FINALIZE_CAP * sizeof(sa_segment)), SA_ERR_MALLOC);
     TRY(ensure(w->d_out, w->out_cap, FINALIZE_CAP, "hsp_out", 1, 1));
+    CU(cudaMalloc((void **)&w->d_dedup, (size_t)kDedupSlots * 20), SA_ERR_MALLOC);
     TRY(ensure(w->d_seeds, w->seeds_cap, std::max<size_t>(G.max_seeds, 1024), "seed_offsets", 1, 1));
     TRY(ensure(w->d_prefix, w->prefix_cap, std::max<size_t>(G.max_seeds, 1024), "hit_num", 1, 1));
     TRY(ensure(w->d_limit_pos, w->limit_cap, 64, "limit_pos", 1, 1));
@@ -257,7 +263,7 @@ int make_workspace(int gpu_index, Workspace *&out) {
 void destroy_workspace(Workspace *w) {
     cudaFree(w->d_seeds); cudaFree(w->d_prefix); cudaFree(w->d_limit_pos);
     cudaFree(w->d_hit_bound); cudaFree(w->d_plan); cudaFree(w->d_counters);
-    cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
+    cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_dedup); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
     cudaFreeHost(w->h_out);
@@ -295,98 +301,117 @@ int sort_anchors(Workspace *w, Anchor *keys, uint32_t n, bool lastz) {
     return SA_OK;
 }
 
-// Seeds are already in w->d_seeds.  Produces the malloc'd result (header + HSPs).
-int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_segment **out,
-                 uint32_t *out_count, PhaseTimer &pt) {
+// Seeds are already in w->d_seeds and their count in w->d_plan[2] (device memory); max_items is
+// the host's upper bound of that count.  Produces the malloc'd result (header + HSPs).
+// Everything between the seeds and the result is enqueued without a host round trip: sizes the
+// host does not know yet (seed count with device seeding, hit count, survivor count, anchor
+// count) are read by the kernels from device memory, buffers are sized from what earlier calls
+// needed, and the one synchronisation at the end tells the host whether a buffer was too small
+// (then it grows the buffer and replays -- rare after the first calls of a block).
+int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_segment **out,
+                 uint32_t *out_count, uint32_t *out_num_seeds, PhaseTimer &pt) {
     GpuCtx &g = G.gpus[w->gpu];
     cudaStream_t st = w->stream;
     uint64_t launches = 0;
-    uint32_t num_hits = 0, num_iter = 0, n_pre = 0, n_final = 0, n_surv = 0;
-    sa_segment *result = nullptr;
+    uint32_t num_hits = 0, num_iter = 0, num_seeds = 0, n_pre = 0, n_final = 0, n_surv = 0;
     unsigned long long ext_cells = 0;
+    const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
+    const bool filter = G.filter_ok && G.use_filter;
+    bool staged = false; // result records already in w->h_out
 
-    // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
-    k_count_hits<<<grid_for(num_seeds, 256), 256, 0, st>>>(w->d_seeds, num_seeds, g.d_index, w->d_prefix);
+    if (!w->d_hits) TRY(ensure(w->d_hits, w->hits_cap, (size_t)1 << 24, "hsp", 1, 1));
+    if (!w->d_surv) TRY(ensure(w->d_surv, w->surv_cap, w->hits_cap, "survivors", 1, 1));
+    if (!w->d_anchors_a) TRY(ensure(w->d_anchors_a, w->anchors_a_cap, (size_t)1 << 20, "hsp_reduced", 1, 1));
     size_t bytes = 0;
-    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)num_seeds, st), SA_ERR_KERNEL);
+    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
     TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
-    CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)num_seeds, st), SA_ERR_KERNEL);
-    launches += 3;
-    // 2. iteration plan on the device (seed_filter.cu:718-745)
-    for (;;) {
-        k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, num_seeds, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
-                                            w->d_limit_pos, w->d_hit_bound, w->d_plan);
-        launches++;
-        CU(cudaMemcpyAsync(w->h_small, w->d_plan, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-        num_iter = w->h_small[0];
-        num_hits = w->h_small[1];
-        if (num_iter != 0xFFFFFFFFu) break;
-        size_t need = (size_t)num_hits / G.max_hits + 2;
-        TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
-        TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
-    }
-    pt.mark(PH_PLAN);
 
-    if (num_hits > 0) {
+    ExtendParams P;
+    P.rb8 = g.ref.b8; P.rp2 = g.ref.p2; P.rm1 = g.ref.m1; P.ref_len = g.ref.len;
+    P.qb8 = q.b8; P.qp2 = q.p2; P.qm1 = q.m1; P.query_len = q.len;
+    P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
+    P.diag_all_positive = G.diag_all_positive;
+    P.scores_fit_int8 = G.filter_ok;
+    FilterParams F;
+    F.rrec = g.ref.rec; F.qrec = q.rec;
+    F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
+    F.k_mul = 4u | (64u << 8); F.k_m4 = 0x01010101u;
+
+    for (int attempt = 0;; attempt++) {
+        if (attempt > 8) return fail(SA_ERR_KERNEL, "SeedAndFilter did not converge on buffer sizes");
+        const uint32_t hits_cap = (uint32_t)std::min<size_t>(std::min(w->hits_cap, w->surv_cap), 0xFFFFFFFFu);
+        const uint32_t anchor_cap = (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu);
+        // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
+        k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, w->d_prefix);
+        CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
+        // 2. iteration plan on the device (seed_filter.cu:718-745)
+        k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, max_items, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
+                                            w->d_limit_pos, w->d_hit_bound, w->d_plan);
+        pt.mark(PH_PLAN);
         // 3. flat hit expansion (seed_filter.cu:760)
-        TRY(ensure(w->d_hits, w->hits_cap, num_hits, "hsp"));
-        k_expand_hits<<<grid_for(((size_t)num_seeds + 31) / 32 * 32, 256), 256, 0, st>>>(
-            w->d_seeds, num_seeds, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits);
-        launches++;
+        k_expand_hits<<<grid_for(((size_t)max_items + 31) / 32 * 32, 256), 256, 0, st>>>(
+            w->d_seeds, max_items, w->d_plan + 2, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits, hits_cap);
         pt.mark(PH_LOOKUP);
-        // 4. extension + append (seed_filter.cu:762-774)
-        ExtendParams P;
-        const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
-        P.rb8 = g.ref.b8; P.rp2 = g.ref.p2; P.rm1 = g.ref.m1; P.ref_len = g.ref.len;
-        P.qb8 = q.b8; P.qp2 = q.p2; P.qm1 = q.m1; P.query_len = q.len;
-        P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
-        P.diag_all_positive = G.diag_all_positive;
-        if (!w->d_anchors_a) TRY(ensure(w->d_anchors_a, w->anchors_a_cap, (size_t)1 << 20, "hsp_reduced", 1, 1));
-        const bool filter = G.filter_ok && G.use_filter;
+        // 4. extension (seed_filter.cu:762-774).  Stage A: conservative score bound over all hits ->
+        //    survivor list (kernels_filter.cuh); stage B: exact extension of the survivors
         CU(cudaMemsetAsync(w->d_counters, 0, 8 * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        DedupTable D;
+        D.k0 = w->d_dedup; D.k1 = w->d_dedup + kDedupSlots;
+        D.tagbits = reinterpret_cast<uint32_t *>(w->d_dedup + 2 * (size_t)kDedupSlots);
+        D.mask = (G.use_dedup && G.hspthresh > 0) ? kDedupSlots - 1 : 0;
+        if (D.mask) {
+            CU(cudaMemsetAsync(w->d_dedup, 0xFF, (size_t)kDedupSlots * 16, st), SA_ERR_MEMCPY);
+            CU(cudaMemsetAsync(D.tagbits, 0, (size_t)kDedupSlots * 4, st), SA_ERR_MEMCPY);
+        }
+        launches += 5;
         if (filter) {
-            // stage A: conservative score bound over all hits -> survivor list (kernels_filter.cuh)
-            TRY(ensure(w->d_surv, w->surv_cap, num_hits, "survivors"));
-            FilterParams F;
-            F.rrec = g.ref.rec; F.qrec = q.rec;
-            F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
-            F.k_mul = 8u | (128u << 8); F.k_m4 = 0x01010101u;
             k_filter_hits<<<G.filter_grid, FILTER_THREADS, FILTER_LUT_WORDS * sizeof(uint32_t), st>>>(
-                F, g.d_sub_mat, w->d_hits, w->d_plan, (uint32_t)std::min<size_t>(w->hits_cap, 0xFFFFFFFFu), w->d_surv, w->d_counters);
+                F, g.d_sub_mat, w->d_hits, w->d_plan, hits_cap, w->d_surv, w->d_counters);
             launches++;
             pt.mark(PH_FILTER);
         }
-        bool staged = false; // result records already in w->h_out
-        for (;;) {
-            // stage B: exact extension (of the survivors, or of every hit without the filter)
-            // (two lanes per work item; with the filter the item count is only known on the device)
-            k_extend_hits<<<grid_for(filter ? std::max<size_t>(num_hits / 32, 8192) : 2 * (size_t)num_hits, 128, 16), 128, 0, st>>>(
-                P, g.d_sub_mat, w->d_hits, num_hits, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
-                w->d_anchors_a, (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu), w->d_counters);
-            pt.mark(PH_EXTEND);
-            // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the
-            //    anchors fit, with the count read on the device; the first FINALIZE_CAP records and
-            //    the counters come back in the same synchronisation
-            k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu),
-                                                             w->d_out, w->d_counters);
-            pt.mark(PH_SORT);
-            launches += 2;
-            CU(cudaMemcpyAsync(w->h_small, w->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-            CU(cudaMemcpyAsync(w->h_out, w->d_out, FINALIZE_CAP * sizeof(sa_segment), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-            CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-            n_pre = w->h_small[CTR_ANCHORS];
-            n_surv = filter ? w->h_small[CTR_SURV] : num_hits;
-            memcpy(&ext_cells, &w->h_small[CTR_EXT_LO], 8);
-            if (n_pre <= w->anchors_a_cap) break;
-            TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced")); // rare: rerun stage B
-            CU(cudaMemsetAsync(w->d_counters, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
+            P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
+            w->d_anchors_a, anchor_cap, w->d_counters, D);
+        pt.mark(PH_EXTEND);
+        // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the anchors
+        //    fit; the counters, the plan and the first FINALIZE_CAP records come back together
+        k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters);
+        pt.mark(PH_SORT);
+        launches += 2;
+        CU(cudaMemcpyAsync(w->h_small, w->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(w->h_small + 8, w->d_plan, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(w->h_out, w->d_out, FINALIZE_CAP * sizeof(sa_segment), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+        num_iter = w->h_small[8];
+        num_hits = w->h_small[9];
+        num_seeds = std::min(w->h_small[10], max_items);
+        n_pre = w->h_small[CTR_ANCHORS];
+        n_surv = filter ? w->h_small[CTR_SURV] : num_hits;
+        memcpy(&ext_cells, &w->h_small[CTR_EXT_LO], 8);
+        if (num_iter == 0xFFFFFFFFu) { // more iterations than the plan arrays hold
+            size_t need = (size_t)num_hits / G.max_hits + 2;
+            TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
+            TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
+            continue;
         }
+        if (num_hits > hits_cap) { // the hit list did not fit: grow and replay
+            TRY(ensure(w->d_hits, w->hits_cap, num_hits, "hsp"));
+            TRY(ensure(w->d_surv, w->surv_cap, w->hits_cap, "survivors", 1, 1));
+            continue;
+        }
+        if (n_pre > anchor_cap) { // the anchor list did not fit
+            TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced"));
+            continue;
+        }
+        break;
+    }
+    if (num_hits > 0) {
         if (w->h_small[CTR_OUT] != 0xFFFFFFFFu) {
             n_final = w->h_small[CTR_OUT];
             staged = true;
         } else {
-            // many anchors (self-alignment, repeat families): device-wide sorts
+            // many anchors (self-alignment, repeat families, long homologous runs): device-wide sorts
             TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
             TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
             CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
@@ -400,27 +425,21 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
             launches += 8;
             pt.mark(PH_SORT);
         }
-        // 6. result (seed_filter.cu:786-788, :804-822)
-        sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
-        if (!res) return fail(SA_ERR_MALLOC, "malloc of result failed");
-        if (staged) {
-            memcpy(res + 1, w->h_out, (size_t)n_final * sizeof(sa_segment));
-        } else if (n_final > 0) {
-            cudaError_t e = cudaMemcpyAsync(res + 1, w->d_out, (size_t)n_final * sizeof(sa_segment), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) {
-                free(res);
-                return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for hsp_output failed with error \" %s \"",
-                            (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
-            }
+    }
+    // 6. result (seed_filter.cu:786-788, :804-822)
+    sa_segment *res = (sa_segment *)malloc(((size_t)n_final + 1) * sizeof(sa_segment));
+    if (!res) return fail(SA_ERR_MALLOC, "malloc of result failed");
+    if (staged) {
+        memcpy(res + 1, w->h_out, (size_t)n_final * sizeof(sa_segment));
+    } else if (n_final > 0) {
+        cudaError_t e = cudaMemcpyAsync(res + 1, w->d_out, (size_t)n_final * sizeof(sa_segment), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            free(res);
+            return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for hsp_output failed with error \" %s \"",
+                        (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
         }
-        result = res;
     }
-    if (!result) { // no hits at all: header only
-        result = (sa_segment *)malloc(sizeof(sa_segment));
-        if (!result) return fail(SA_ERR_MALLOC, "malloc of result failed");
-    }
-    sa_segment *res = result;
     res[0].ref_start = 0;
     res[0].query_start = 0;
     res[0].len = n_final;
@@ -430,6 +449,7 @@ int run_pipeline(Workspace *w, uint32_t num_seeds, int rev, uint32_t buffer, sa_
     CU(cudaGetLastError(), SA_ERR_KERNEL);
     *out = res;
     *out_count = n_final + 1;
+    if (out_num_seeds) *out_num_seeds = num_seeds;
     {
         std::lock_guard<std::mutex> l(G.stats_mu);
         sa_stats &s = G.stats;
@@ -519,6 +539,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     }
     const char *fenv = getenv("SEGALIGN_B200_FILTER");
     G.use_filter = !(fenv && atoi(fenv) == 0);
+    const char *denv = getenv("SEGALIGN_B200_DEDUP");
+    G.use_dedup = !(denv && atoi(denv) == 0);
     const char *env = getenv("SEGALIGN_B200_STREAMS");
     if (env && atoi(env) > 0) G.ws_per_gpu = atoi(env);
     for (size_t i = 0; i < G.gpus.size(); i++) {
@@ -531,6 +553,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
                                                          FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device), SA_ERR_KERNEL);
         G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
+        G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
         for (SeqPlanes *p : all)
@@ -740,8 +763,10 @@ int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint3
     TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
     TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
     CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    w->h_small[12] = num_seeds; // pinned: the seed count travels to d_plan[2] on the stream
+    CU(cudaMemcpyAsync(w->d_plan + 2, w->h_small + 12, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
     pt.mark(PH_SEEDS);
-    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
+    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, nullptr, pt);
 }
 
 int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev,
@@ -758,42 +783,36 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
     if (q_end > q.len) return fail(SA_ERR_ARG, "range [%u,%u) exceeds the query block (%u)", q_start, q_end, q.len);
     PhaseTimer pt(w);
     pt.mark(PH_START);
-    uint32_t n = q_end - q_start, num_seeds = 0;
+    const uint32_t n = q_end - q_start;
     const uint32_t per = 1u + (transition ? (uint32_t)G.shape.num_trans : 0u);
-    if (n > 0) {
-        cudaStream_t st = w->stream;
-        TRY(ensure(w->d_flags, w->flags_cap, n, "seed_flags"));
-        TRY(ensure(w->d_excl, w->excl_cap, (size_t)n + 1, "seed_excl"));
-        k_seed_flags<<<grid_for(n, 256), 256, 0, st>>>(q.m1, G.shape.span, q_start, q_end, w->d_flags);
-        size_t bytes = 0;
-        CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
-        TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
-        CU(cub::DeviceScan::ExclusiveSum(w->d_temp, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
-        CU(cudaMemcpyAsync(w->h_small, w->d_excl + (n - 1), 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-        CU(cudaMemcpyAsync(w->h_small + 1, w->d_flags + (n - 1), 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-        uint32_t valid = w->h_small[0] + w->h_small[1];
-        num_seeds = valid * per;
-        add_launches(3);
-        if (num_seeds > G.max_seeds) {
-            printf("MAX_SEEDS exceeded\n");
-            return fail(SA_ERR_MAX_SEEDS, "num_seeds %u > MAX_SEEDS %u", num_seeds, G.max_seeds);
-        }
-        if (num_seeds > 0) {
-            TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
-            TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
-            k_seed_emit<<<grid_for(n, 256), 256, 0, st>>>(q.p2, w->d_flags, w->d_excl, G.shape, transition, q_start, q_end, w->d_seeds);
-            add_launches(1);
-        }
-    }
-    if (out_num_seeds) *out_num_seeds = num_seeds;
-    if (num_seeds == 0) {
+    const uint64_t max_items64 = (uint64_t)n * per;
+    if (n == 0) {
+        if (out_num_seeds) *out_num_seeds = 0;
         sa_segment *res = (sa_segment *)calloc(1, sizeof(sa_segment));
         *out = res; *out_count = 1;
         return SA_OK;
     }
+    if (max_items64 > G.max_seeds) { // a full range could exceed MAX_SEEDS (seed_filter.cu:688-692)
+        printf("MAX_SEEDS exceeded\n");
+        return fail(SA_ERR_MAX_SEEDS, "range of %u positions x %u words > MAX_SEEDS %u", n, per, G.max_seeds);
+    }
+    const uint32_t max_items = (uint32_t)max_items64;
+    cudaStream_t st = w->stream;
+    TRY(ensure(w->d_flags, w->flags_cap, n, "seed_flags"));
+    TRY(ensure(w->d_excl, w->excl_cap, (size_t)n + 1, "seed_excl"));
+    TRY(ensure(w->d_seeds, w->seeds_cap, max_items, "seed_offsets"));
+    TRY(ensure(w->d_prefix, w->prefix_cap, max_items, "hit_num"));
+    size_t bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
+    // seed words of src/seeder.cpp:57-74 on the device; their count stays on the device (d_plan[2])
+    k_seed_flags<<<grid_for(n, 256), 256, 0, st>>>(q.m1, G.shape.span, q_start, q_end, w->d_flags);
+    CU(cub::DeviceScan::ExclusiveSum(w->d_temp, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+    k_seed_emit<<<grid_for(n, 256), 256, 0, st>>>(q.p2, w->d_flags, w->d_excl, G.shape, transition, q_start, q_end,
+                                                  w->d_seeds, w->d_plan + 2);
+    add_launches(4);
     pt.mark(PH_SEEDS);
-    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, pt);
+    return run_pipeline(w, max_items, rev, buffer, out, out_count, out_num_seeds, pt);
 }
 
 void sa_release_result(sa_segment *out) { free(out); }

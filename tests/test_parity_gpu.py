@@ -30,6 +30,16 @@ def test_exact_stage_alone_matches_reference_golden(backend, case, monkeypatch):
     H.assert_calls_equal(got, want, "exact stage alone vs reference golden")
 
 
+@pytest.mark.parametrize("name", ["repeats_entropy", "diverged_multi_iter", "self_align", "iupac_both_strands"])
+def test_without_duplicate_table_matches_reference_golden(backend, name, monkeypatch):
+    """SEGALIGN_B200_DEDUP=0: every passing record reaches the sort (the reference's own flow)."""
+    monkeypatch.setenv("SEGALIGN_B200_DEDUP", "0")
+    case = H.CASES_BY_NAME[name]
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case)
+    H.assert_calls_equal(got, want, "no duplicate table vs reference golden")
+
+
 def test_filter_keeps_a_small_superset(backend):
     """The filter's survivors are few (it is the point of the stage) and contain every HSP."""
     case = H.CASES_BY_NAME["masked_multichrom"]
