@@ -15,6 +15,7 @@
 //   * passing HSPs are appended with an atomic cursor (order is irrelevant, A.8) instead of
 //     flag-scan + compaction over all hits.
 #pragma once
+#include "kernels_filter.cuh"
 #include "sa_common.cuh"
 
 namespace sa {
@@ -249,11 +250,6 @@ __device__ __forceinline__ uint32_t iteration_of(const uint32_t *__restrict__ hi
     return lo;
 }
 
-// counters[0] = anchor cursor, counters[2..3] = ext_cells (64-bit), counters[4] = survivor count.
-// With surv != nullptr the kernel walks the survivor list of the filter kernel (hit indices,
-// count read from counters[4] on the device so the host need not synchronise in between);
-// otherwise it walks hits [0, h_end) directly.  Lanes 2i / 2i+1 of a warp extend work item i to
-// the right / to the left.
 // Exact-duplicate suppression at append time.  Every seed hit inside one homologous run extends
 // to the same HSP, so ~99 % of the passing records of a call are byte-identical copies.  Removing
 // identical records (same iteration tag) before the diagonal sort cannot change the reference's
@@ -286,9 +282,17 @@ __device__ __forceinline__ bool dedup_is_new(const DedupTable &T, const sa_segme
 
 constexpr int EXTEND_THREADS = 32; // one warp per block: fits beside the resident filter blocks
 
+// counters: see the CTR_* enum (kernels_filter.cuh).
+// With surv != nullptr the kernel walks the survivor records of the filter kernel (their count is
+// read from counters[CTR_SURV] on the device so the host need not synchronise in between);
+// otherwise it walks hits [0, min(plan[1], h_end)) directly.  Lanes 2i / 2i+1 of a warp extend work
+// item i to the right / to the left.
+// Iteration tag of a hit (dedupe scope): general path = position of the hit index in
+// the plan's hit bounds; fused path (one iteration pair, num_hits < MAX_HITS) = 0 for hits of seed
+// words before the last hit-bearing seed word, 1 from that seed word on.
 __global__ void __launch_bounds__(EXTEND_THREADS)
 k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              uint32_t h_end, const uint32_t *__restrict__ surv,
+              uint32_t h_end, const SurvRec *__restrict__ surv, uint32_t surv_cap, int fused,
               const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors,
               uint32_t anchor_cap, uint32_t *__restrict__ counters, DedupTable dedup) {
@@ -299,7 +303,7 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
     if (threadIdx.x < 16) lut16[threadIdx.x] = sub_mat[(threadIdx.x >> 2) * 8 + (threadIdx.x & 3)];
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
-    h_end = surv ? counters[4] : min(plan[1], h_end); // counts known only on the device
+    h_end = surv ? min(counters[CTR_SURV], surv_cap) : min(plan[1], h_end); // counts known only on the device
     const uint32_t items_per_pass = (gridDim.x * blockDim.x) >> 1;
     const bool left = threadIdx.x & 1u;
     unsigned long long cells = 0;
@@ -315,8 +319,8 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
 #pragma unroll
         for (int c = 0; c < 4; c++) { C.cnt[c] = 0; C.del[c] = 0; }
         if (valid) {
-            h = surv ? surv[i] : i;
-            hit = hits[h];
+            if (surv) { const SurvRec rec = surv[i]; h = rec.key; hit = make_uint2(rec.r0, rec.q0); }
+            else { h = i; hit = hits[i]; }
             D = extend_dir(P, sub, lut16, diag, hit.x, hit.y, left, C, &cells);
         }
         // the right lane (even) receives the left lane's result
@@ -330,7 +334,8 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
             sa_segment seg;
             uint32_t tag = 0;
             if (finish_hit(P, hit.x, hit.y, D, L, cnt, &seg) &&
-                dedup_is_new(dedup, seg, tag = iteration_of(hit_bound, plan[0], h))) {
+                dedup_is_new(dedup, seg, tag = fused ? (h >= counters[CTR_LASTKEY] ? 1u : 0u)
+                                                  : iteration_of(hit_bound, plan[0], h))) {
                 uint32_t slot = atomicAdd(counters, 1u);
                 if (slot < anchor_cap) {
                     Anchor a;

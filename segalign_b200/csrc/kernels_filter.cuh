@@ -51,7 +51,11 @@ struct FilterParams {
 };
 
 // counters layout shared with the host (uint32 words)
-enum { CTR_ANCHORS = 0, CTR_DEDUPE = 1, CTR_EXT_LO = 2, CTR_EXT_HI = 3, CTR_SURV = 4, CTR_CHUNK = 5, CTR_OUT = 6 };
+enum { CTR_ANCHORS = 0, CTR_DEDUPE = 1, CTR_EXT_LO = 2, CTR_EXT_HI = 3, CTR_SURV = 4, CTR_CHUNK = 5, CTR_OUT = 6,
+       CTR_NHITS = 7,    // fused sources: total seed hits of the call
+       CTR_LASTKEY = 8,  // fused sources: seed order index of the last seed word with a non-empty bucket
+       CTR_NSEEDS = 9,   // fused sources: number of seed words
+       CTR_WORDS = 16 };
 
 // 32 cells starting at cell c (may be negative / past the end: the pads are terminators).
 // R: 2-bit codes, cell i at bits 2i.  T: terminator bits.  S: soft (non-ACGT, non-terminator) bits.
@@ -104,10 +108,41 @@ __device__ __forceinline__ uint32_t group_scores(uint32_t lut_lane, uint32_t mul
     return __byte_perm(lds_u32(oa), lds_u32(ob), 0x5410);
 }
 
+// Where the hits of a call come from.
+//   SRC_HITS : the materialised hit list of k_expand_hits (general path: any number of iterations)
+//   SRC_SEEDS: straight from the caller's seed words  -- lookup, expansion and filter fused
+//   SRC_RANGE: straight from the resident query block -- seeding, lookup, expansion and filter fused
+// The fused sources never write the seed words' hit counts, their prefix sums or the hit list to
+// HBM; they are valid when the whole call is one reference "iteration pair" (num_hits < MAX_HITS,
+// SURVEY A.7), which the host checks from the hit total this kernel reports.
+enum { SRC_HITS = 0, SRC_SEEDS = 1, SRC_RANGE = 2 };
+
+struct HitSource {
+    // SRC_HITS
+    const uint2 *hits;
+    const uint32_t *plan;      // plan[1] = num_hits
+    uint32_t hits_cap;
+    // SRC_SEEDS / SRC_RANGE
+    const uint64_t *seeds;     // seed words (kmer << 32) + query position
+    uint32_t num_items;        // seed words, or (positions x words per position) for SRC_RANGE
+    const uint32_t *index_table;
+    const uint32_t *pos_table;
+    uint32_t seed_size;
+    // SRC_RANGE: seed words of src/seeder.cpp:57-74 generated on the fly
+    uint32_t j0;               // first query position of the range
+    uint32_t per;              // words per valid position: 1 + transition variants
+    ShapeDesc shape;
+};
+
+// survivor of the filter: anchor pair + key (hit index for SRC_HITS, seed order index otherwise)
+struct SurvRec {
+    uint32_t r0, q0, key;
+};
+
+template <int SRC>
 __global__ void __launch_bounds__(FILTER_THREADS, 6)
-k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              const uint32_t *__restrict__ plan, uint32_t hits_cap, uint32_t *__restrict__ surv,
-              uint32_t *__restrict__ counters) {
+k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, SurvRec *__restrict__ surv,
+              uint32_t surv_cap, uint32_t *__restrict__ counters) {
     extern __shared__ uint32_t lut[];
     __shared__ int diag[4];
     for (int i = threadIdx.x; i < FILTER_LUT_WORDS; i += blockDim.x) {
@@ -118,7 +153,6 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
 
-    const uint32_t num_hits = min(plan[1], hits_cap);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     // shared-space address of this lane's LUT column and the loop constants, pinned in registers
@@ -127,45 +161,133 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
     const uint32_t mul = P.k_mul, m4 = P.k_m4;
     const int X = P.xdrop;
 
-    // Work distribution: a warp grabs FILTER_CHUNK consecutive hits at a time from a global
-    // counter (fine-grained, so that all warps finish together) and stages them in shared memory
-    // with one coalesced load; lanes then pick hits from the staged chunk as they become free.
+    // Work distribution: a warp stages up to FILTER_CHUNK hits at a time in shared memory and its
+    // lanes pick hits from the staged chunk as they become free.  SRC_HITS: a chunk is a slice of
+    // the hit list (one coalesced load).  Fused sources: the warp grabs 32 consecutive seed words
+    // from a global counter, looks their buckets up and expands them, FILTER_CHUNK hits at a time.
     __shared__ uint2 hitbuf[FILTER_THREADS / 32][FILTER_CHUNK];
+    __shared__ uint8_t ownbuf[FILTER_THREADS / 32][FILTER_CHUNK];
     uint2 *mybuf = hitbuf[threadIdx.x >> 5];
-    uint32_t chunk_start = 0, cursor = 0, limit = 0; // warp-uniform: current chunk [chunk_start, limit), next unassigned hit
-    bool exhausted = false;                          // warp-uniform: the global chunk counter ran past num_hits
+    uint8_t *myown = ownbuf[threadIdx.x >> 5];
+    const uint32_t total_items = SRC == SRC_HITS ? min(H.plan[1], H.hits_cap) : H.num_items;
+    uint32_t key_base = 0;            // warp-uniform: hit index of staged slot 0 / seed index of the group's lane 0
+    uint32_t cursor = 0, limit = 0;   // warp-uniform: staged slots [cursor, limit) are unassigned
+    uint32_t g_total = 0, g_done = 0; // warp-uniform (fused): hits of the current seed group, hits already staged
+    bool exhausted = false;           // warp-uniform: the global work counter ran past the end
+    uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0; // per-warp totals (fused), flushed once at the end
+    bool any_hits = false;
     // current hit of this lane
     bool active = false, left = false;
-    uint32_t h = 0, r0 = 0, q0 = 0, t = 0;
+    uint32_t key = 0, r0 = 0, q0 = 0, t = 0;
     int s = 0, M = 0, right_score = 0;
     unsigned long long ext_cells = 0;
 
     for (;;) {
         const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
         if (need && !exhausted) {
-            if (cursor == limit) { // chunk used up: grab and stage the next one
-                uint32_t c = 0;
-                if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
-                c = __shfl_sync(0xFFFFFFFFu, c, 0);
-                const unsigned long long start = (unsigned long long)c * FILTER_CHUNK;
-                chunk_start = start < num_hits ? (uint32_t)start : num_hits;
-                limit = (num_hits - chunk_start < FILTER_CHUNK) ? num_hits : chunk_start + FILTER_CHUNK;
-                cursor = chunk_start;
-                exhausted = cursor == limit;
-                __syncwarp();
+            while (cursor == limit && !exhausted) { // staged chunk used up: stage the next one
+                if (SRC == SRC_HITS) {
+                    uint32_t c = 0;
+                    if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
+                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                    const unsigned long long start = (unsigned long long)c * FILTER_CHUNK;
+                    key_base = start < total_items ? (uint32_t)start : total_items;
+                    const uint32_t cnt = min(total_items - key_base, FILTER_CHUNK);
+                    exhausted = cnt == 0;
+                    __syncwarp();
 #pragma unroll
-                for (uint32_t k = 0; k < FILTER_CHUNK / 32; k++) {
-                    const uint32_t i = chunk_start + k * 32u + lane;
-                    if (i < limit) mybuf[k * 32u + lane] = __ldg(hits + i);
+                    for (uint32_t k = 0; k < FILTER_CHUNK / 32; k++)
+                        if (k * 32u + lane < cnt) mybuf[k * 32u + lane] = __ldg(H.hits + key_base + k * 32u + lane);
+                    __syncwarp();
+                    cursor = 0; limit = cnt;
+                } else {
+                    if (g_done == g_total) { // next group of 32 seed words
+                        uint32_t c = 0;
+                        if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
+                        c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                        const unsigned long long start = (unsigned long long)c * 32u;
+                        if (start >= total_items) { exhausted = true; break; }
+                        key_base = (uint32_t)start;
+                        g_done = 0;
+                        g_total = 0xFFFFFFFFu; // computed below together with the lanes' buckets
+                    }
+                    // this lane's seed word and bucket (recomputed per staged chunk: cheaper than
+                    // keeping five more registers alive across the extension trips)
+                    const uint32_t k = key_base + lane;
+                    uint32_t b_start = 0, n = 0, qa = 0;
+                    bool valid = false;
+                    if (k < total_items) {
+                        uint32_t kmer = 0, qpos = 0;
+                        if (SRC == SRC_SEEDS) {
+                            const uint64_t word = __ldg(H.seeds + k);
+                            kmer = (uint32_t)(word >> 32); qpos = (uint32_t)word;
+                            valid = true;
+                        } else {
+                            const uint32_t pi = k / H.per, v = k - pi * H.per;
+                            qpos = H.j0 + pi;
+                            uint64_t W; uint32_t Tw, Sw;
+                            load_window(P.qrec, (int)qpos, W, Tw, Sw);
+                            const uint32_t span_mask = H.shape.span >= 32 ? 0xFFFFFFFFu : ((1u << H.shape.span) - 1u);
+                            valid = ((Tw | Sw) & span_mask) == 0; // all span cells upper-case ACGT (ntcoding.cpp:47-52)
+                            for (int i = 0; i < H.shape.weight; i++) kmer = (kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
+                            if (v > 0) kmer ^= 2u << (2 * H.shape.tvar[v - 1]); // seeder.cpp:64-71
+                        }
+                        if (valid) {
+                            const uint32_t b_end = __ldg(H.index_table + kmer);
+                            b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                            n = b_end - b_start;
+                            qa = qpos + H.seed_size;
+                        }
+                    }
+                    uint32_t incl = n;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                        if (lane >= (uint32_t)off) incl += up;
+                    }
+                    const uint32_t excl = incl - n;
+                    if (g_total == 0xFFFFFFFFu) { // first visit of this group: account for it
+                        g_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        acc_hits += g_total;
+                        acc_seeds += __popc(__ballot_sync(0xFFFFFFFFu, valid));
+                        const unsigned with_hits = __ballot_sync(0xFFFFFFFFu, n > 0);
+                        if (with_hits) { acc_last = key_base + (31u - __clz(with_hits)); any_hits = true; } // groups come in ascending order per warp
+                        if (g_total == 0) continue;
+                    }
+                    const uint32_t cnt = min(g_total - g_done, FILTER_CHUNK);
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t kk = 0; kk < FILTER_CHUNK / 32; kk++) {
+                        const uint32_t f = g_done + kk * 32u + lane; // flat index inside the group
+                        // owner = first lane whose inclusive prefix exceeds f
+                        uint32_t lo = 0, hi = 31;
+#pragma unroll
+                        for (int it = 0; it < 5; it++) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            const uint32_t vmid = __shfl_sync(0xFFFFFFFFu, incl, mid);
+                            if (vmid > f) hi = mid; else lo = mid + 1;
+                        }
+                        const uint32_t o_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
+                        const uint32_t o_start = __shfl_sync(0xFFFFFFFFu, b_start, lo);
+                        const uint32_t o_q = __shfl_sync(0xFFFFFFFFu, qa, lo);
+                        if (kk * 32u + lane < cnt) {
+                            const uint32_t r = __ldg(H.pos_table + o_start + (f - o_excl)) + H.seed_size;
+                            mybuf[kk * 32u + lane] = make_uint2(r, o_q);
+                            myown[kk * 32u + lane] = (uint8_t)lo;
+                        }
+                    }
+                    __syncwarp();
+                    g_done += cnt;
+                    cursor = 0; limit = cnt;
                 }
-                __syncwarp();
             }
             const uint32_t avail = limit - cursor;
             const uint32_t rank = __popc(need & lt_mask);
             if (!active && rank < avail) {
-                h = cursor + rank;
-                const uint2 hit = mybuf[h - chunk_start];
+                const uint32_t slot = cursor + rank;
+                const uint2 hit = mybuf[slot];
                 r0 = hit.x; q0 = hit.y;
+                key = key_base + (SRC == SRC_HITS ? slot : (uint32_t)myown[slot]);
                 active = true; left = false; t = 0; s = 0; M = 0;
             }
             const uint32_t nneed = __popc(need);
@@ -232,23 +354,33 @@ k_filter_hits(FilterParams P, const int *__restrict__ sub_mat, const uint2 *__re
             }
             const bool done = dropped || n_eff < 32;
             if (t >= 32u) ext_cells += 32;
+            bool emit = false;
             if (survive) {
-                surv[atomicAdd(counters + CTR_SURV, 1u)] = h;
+                emit = true;
                 active = false;
             } else if (done) {
                 if (!left) {
                     right_score = M;
                     left = true; t = 0; s = 0; M = 0;
                 } else {
-                    if (right_score + M >= P.hspthresh) surv[atomicAdd(counters + CTR_SURV, 1u)] = h;
+                    emit = right_score + M >= P.hspthresh;
                     active = false;
                 }
             } else {
                 t += 32u;
             }
+            if (emit) {
+                const uint32_t slot = atomicAdd(counters + CTR_SURV, 1u);
+                if (slot < surv_cap) { SurvRec rec; rec.r0 = r0; rec.q0 = q0; rec.key = key; surv[slot] = rec; }
+            }
         }
     }
     if (ext_cells) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), ext_cells);
+    if (SRC != SRC_HITS && lane == 0) {
+        if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits); // uint32 wrap-around like the reference's scan
+        if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
+        if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
+    }
 }
 
 // ASCII-independent record builder: b8 -> {p2 lo, p2 hi, terminator bits, soft bits} per 32 bases.

@@ -92,9 +92,9 @@ struct Workspace {
     uint32_t *d_limit_pos = nullptr; size_t limit_cap = 0;
     uint32_t *d_hit_bound = nullptr; size_t bound_cap = 0;
     uint32_t *d_plan = nullptr;      // [0]=num_iter [1]=num_hits
-    uint32_t *d_counters = nullptr;  // [0]=anchor cursor [1]=dedupe cursor [2..3]=ext cells
+    uint32_t *d_counters = nullptr;  // CTR_WORDS counters, see the CTR_* enum (kernels_filter.cuh)
     uint2 *d_hits = nullptr; size_t hits_cap = 0;
-    uint32_t *d_surv = nullptr; size_t surv_cap = 0; // filter survivors (hit indices)
+    SurvRec *d_surv = nullptr; size_t surv_cap = 0;  // filter survivors (anchor pair + key)
     unsigned long long *d_dedup = nullptr;           // exact-duplicate table: k0[slots], k1[slots], tagbits[slots]
     Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
     Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
@@ -102,7 +102,7 @@ struct Workspace {
     uint8_t *d_temp = nullptr; size_t temp_cap = 0;
     uint32_t *d_flags = nullptr; size_t flags_cap = 0;
     uint32_t *d_excl = nullptr; size_t excl_cap = 0;
-    uint32_t *h_small = nullptr; // pinned, 16 words
+    uint32_t *h_small = nullptr; // pinned, 64 words: [0..15] counters, [16..19] plan, [20] seed count staging
     sa_segment *h_out = nullptr; // pinned staging for the first FINALIZE_CAP result records
 };
 
@@ -129,6 +129,7 @@ struct Global {
     bool filter_ok = false;    // ACGT x ACGT scores fit int8: the filter stage is usable
     bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
+    bool use_fused = true;     // SEGALIGN_B200_FUSED=0 always takes the general (materialised hit list) path
     int filter_grid = 0;
     int extend_grid = 0;
     uint32_t ref_len = 0;
@@ -247,8 +248,8 @@ int make_workspace(int gpu_index, Workspace *&out) {
     CU(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking), SA_ERR_KERNEL);
     for (auto &e : w->ev) CU(cudaEventCreate(&e), SA_ERR_KERNEL);
     CU(cudaMalloc((void **)&w->d_plan, 4 * sizeof(uint32_t)), SA_ERR_MALLOC);
-    CU(cudaMalloc((void **)&w->d_counters, 8 * sizeof(uint32_t)), SA_ERR_MALLOC);
-    CU(cudaMallocHost((void **)&w->h_small, 16 * sizeof(uint32_t)), SA_ERR_MALLOC);
+    CU(cudaMalloc((void **)&w->d_counters, CTR_WORDS * sizeof(uint32_t)), SA_ERR_MALLOC);
+    CU(cudaMallocHost((void **)&w->h_small, 64 * sizeof(uint32_t)), SA_ERR_MALLOC);
     CU(cudaMallocHost((void **)&w->h_out, FINALIZE_CAP * sizeof(sa_segment)), SA_ERR_MALLOC);
     TRY(ensure(w->d_out, w->out_cap, FINALIZE_CAP, "hsp_out", 1, 1));
     CU(cudaMalloc((void **)&w->d_dedup, (size_t)kDedupSlots * 20), SA_ERR_MALLOC);
@@ -301,14 +302,48 @@ int sort_anchors(Workspace *w, Anchor *keys, uint32_t n, bool lastz) {
     return SA_OK;
 }
 
-// Seeds are already in w->d_seeds and their count in w->d_plan[2] (device memory); max_items is
-// the host's upper bound of that count.  Produces the malloc'd result (header + HSPs).
-// Everything between the seeds and the result is enqueued without a host round trip: sizes the
-// host does not know yet (seed count with device seeding, hit count, survivor count, anchor
-// count) are read by the kernels from device memory, buffers are sized from what earlier calls
-// needed, and the one synchronisation at the end tells the host whether a buffer was too small
+// What one SeedAndFilter call works on.
+struct CallInput {
+    int src;             // SRC_SEEDS: seed words already in w->d_seeds, count in d_plan[2];  SRC_RANGE: query range
+    uint32_t max_items;  // seed words (SRC_SEEDS) or positions x words per position (SRC_RANGE)
+    uint32_t q_start, q_end, per; // SRC_RANGE
+    int transition;
+};
+
+// SRC_RANGE, general path only: seed words of src/seeder.cpp:57-74 on the device; their count
+// stays on the device (d_plan[2]).
+int enqueue_range_seeding(Workspace *w, const SeqPlanes &q, const CallInput &in) {
+    cudaStream_t st = w->stream;
+    const uint32_t n = in.q_end - in.q_start;
+    TRY(ensure(w->d_flags, w->flags_cap, n, "seed_flags"));
+    TRY(ensure(w->d_excl, w->excl_cap, (size_t)n + 1, "seed_excl"));
+    TRY(ensure(w->d_seeds, w->seeds_cap, in.max_items, "seed_offsets"));
+    size_t bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
+    k_seed_flags<<<grid_for(n, 256), 256, 0, st>>>(q.m1, G.shape.span, in.q_start, in.q_end, w->d_flags);
+    CU(cub::DeviceScan::ExclusiveSum(w->d_temp, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
+    k_seed_emit<<<grid_for(n, 256), 256, 0, st>>>(q.p2, w->d_flags, w->d_excl, G.shape, in.transition, in.q_start, in.q_end,
+                                                  w->d_seeds, w->d_plan + 2);
+    add_launches(4);
+    return SA_OK;
+}
+
+// One SeedAndFilter call.  Produces the malloc'd result (header + HSPs).
+//
+// Fast path (the filter stage is usable): ONE kernel does seeding (SRC_RANGE) / seed-word reading
+// (SRC_SEEDS), seed-position-table lookup, bucket expansion and the score filter; it is followed by
+// the exact extension of the survivors and a one-block sort/dedupe/sort, and by a single
+// synchronisation that brings back the counters and the records.  Hit counts, prefix sums and the
+// hit list are never written to HBM.  It is valid when the call is one reference iteration pair
+// (num_hits < MAX_HITS), which is known from the hit total after the fact; otherwise --
+// or when the filter is disabled -- the call is (re)played on the general path: hit counts -> scan
+// -> iteration plan -> materialised hit list -> filter -> exact, any number of iterations.
+// Either way nothing between the seeds and the result needs a host round trip: sizes the host does
+// not know yet are read by the kernels from device memory, buffers are sized from what earlier
+// calls needed, and the synchronisation at the end tells the host whether a buffer was too small
 // (then it grows the buffer and replays -- rare after the first calls of a block).
-int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_segment **out,
+int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa_segment **out,
                  uint32_t *out_count, uint32_t *out_num_seeds, PhaseTimer &pt) {
     GpuCtx &g = G.gpus[w->gpu];
     cudaStream_t st = w->stream;
@@ -317,14 +352,13 @@ int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_
     unsigned long long ext_cells = 0;
     const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
     const bool filter = G.filter_ok && G.use_filter;
-    bool staged = false; // result records already in w->h_out
+    bool fused = filter && G.use_fused;
+    bool seeds_ready = in.src == SRC_SEEDS; // seed words in d_seeds, count in d_plan[2]
+    bool staged = false;                    // result records already in w->h_out
+    const uint32_t max_items = in.max_items;
 
-    if (!w->d_hits) TRY(ensure(w->d_hits, w->hits_cap, (size_t)1 << 24, "hsp", 1, 1));
-    if (!w->d_surv) TRY(ensure(w->d_surv, w->surv_cap, w->hits_cap, "survivors", 1, 1));
+    if (!w->d_surv) TRY(ensure(w->d_surv, w->surv_cap, (size_t)1 << 20, "survivors", 1, 1));
     if (!w->d_anchors_a) TRY(ensure(w->d_anchors_a, w->anchors_a_cap, (size_t)1 << 20, "hsp_reduced", 1, 1));
-    size_t bytes = 0;
-    CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
-    TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
 
     ExtendParams P;
     P.rb8 = g.ref.b8; P.rp2 = g.ref.p2; P.rm1 = g.ref.m1; P.ref_len = g.ref.len;
@@ -336,42 +370,70 @@ int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_
     F.rrec = g.ref.rec; F.qrec = q.rec;
     F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
     F.k_mul = 4u | (64u << 8); F.k_m4 = 0x01010101u;
+    HitSource H = {};
+    H.plan = w->d_plan;
+    H.num_items = max_items;
+    H.index_table = g.d_index; H.pos_table = g.d_pos; H.seed_size = G.seed_size;
+    H.j0 = in.q_start; H.per = in.per; H.shape = G.shape;
+    DedupTable D;
+    D.k0 = w->d_dedup; D.k1 = w->d_dedup + kDedupSlots;
+    D.tagbits = reinterpret_cast<uint32_t *>(w->d_dedup + 2 * (size_t)kDedupSlots);
+    D.mask = (G.use_dedup && G.hspthresh > 0) ? kDedupSlots - 1 : 0;
+    const size_t lut_bytes = FILTER_LUT_WORDS * sizeof(uint32_t);
 
     for (int attempt = 0;; attempt++) {
-        if (attempt > 8) return fail(SA_ERR_KERNEL, "SeedAndFilter did not converge on buffer sizes");
-        const uint32_t hits_cap = (uint32_t)std::min<size_t>(std::min(w->hits_cap, w->surv_cap), 0xFFFFFFFFu);
+        if (attempt > 12) return fail(SA_ERR_KERNEL, "SeedAndFilter did not converge on buffer sizes");
+        const uint32_t surv_cap = (uint32_t)std::min<size_t>(w->surv_cap, 0xFFFFFFFFu);
         const uint32_t anchor_cap = (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu);
-        // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
-        k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, w->d_prefix);
-        CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
-        // 2. iteration plan on the device (seed_filter.cu:718-745)
-        k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, max_items, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
-                                            w->d_limit_pos, w->d_hit_bound, w->d_plan);
-        pt.mark(PH_PLAN);
-        // 3. flat hit expansion (seed_filter.cu:760)
-        k_expand_hits<<<grid_for(((size_t)max_items + 31) / 32 * 32, 256), 256, 0, st>>>(
-            w->d_seeds, max_items, w->d_plan + 2, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits, hits_cap);
-        pt.mark(PH_LOOKUP);
-        // 4. extension (seed_filter.cu:762-774).  Stage A: conservative score bound over all hits ->
-        //    survivor list (kernels_filter.cuh); stage B: exact extension of the survivors
-        CU(cudaMemsetAsync(w->d_counters, 0, 8 * sizeof(uint32_t), st), SA_ERR_MEMCPY);
-        DedupTable D;
-        D.k0 = w->d_dedup; D.k1 = w->d_dedup + kDedupSlots;
-        D.tagbits = reinterpret_cast<uint32_t *>(w->d_dedup + 2 * (size_t)kDedupSlots);
-        D.mask = (G.use_dedup && G.hspthresh > 0) ? kDedupSlots - 1 : 0;
+        uint32_t hits_cap = 0;
+        CU(cudaMemsetAsync(w->d_counters, 0, CTR_WORDS * sizeof(uint32_t), st), SA_ERR_MEMCPY);
         if (D.mask) {
             CU(cudaMemsetAsync(w->d_dedup, 0xFF, (size_t)kDedupSlots * 16, st), SA_ERR_MEMCPY);
             CU(cudaMemsetAsync(D.tagbits, 0, (size_t)kDedupSlots * 4, st), SA_ERR_MEMCPY);
         }
-        launches += 5;
-        if (filter) {
-            k_filter_hits<<<G.filter_grid, FILTER_THREADS, FILTER_LUT_WORDS * sizeof(uint32_t), st>>>(
-                F, g.d_sub_mat, w->d_hits, w->d_plan, hits_cap, w->d_surv, w->d_counters);
+        if (fused) {
+            H.seeds = w->d_seeds;
+            if (in.src == SRC_SEEDS)
+                k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+            else
+                k_filter_hits<SRC_RANGE><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
             launches++;
             pt.mark(PH_FILTER);
+        } else {
+            if (!seeds_ready) {
+                TRY(enqueue_range_seeding(w, q, in));
+                seeds_ready = true;
+                pt.mark(PH_SEEDS);
+            }
+            if (!w->d_hits) TRY(ensure(w->d_hits, w->hits_cap, (size_t)1 << 25, "hsp", 1, 1));
+            hits_cap = (uint32_t)std::min<size_t>(w->hits_cap, 0xFFFFFFFFu);
+            TRY(ensure(w->d_prefix, w->prefix_cap, max_items, "hit_num"));
+            size_t bytes = 0;
+            CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
+            TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
+            // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
+            k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, w->d_prefix);
+            CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
+            // 2. iteration plan on the device (seed_filter.cu:718-745)
+            k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, max_items, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
+                                                w->d_limit_pos, w->d_hit_bound, w->d_plan);
+            pt.mark(PH_PLAN);
+            // 3. flat hit expansion (seed_filter.cu:760)
+            k_expand_hits<<<grid_for(((size_t)max_items + 31) / 32 * 32, 256), 256, 0, st>>>(
+                w->d_seeds, max_items, w->d_plan + 2, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits, hits_cap);
+            pt.mark(PH_LOOKUP);
+            launches += 5;
+            // 4a. stage A: conservative score bound over all hits -> survivor records
+            if (filter) {
+                H.hits = w->d_hits; H.hits_cap = hits_cap;
+                k_filter_hits<SRC_HITS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                launches++;
+                pt.mark(PH_FILTER);
+            }
         }
+        // 4b. stage B: exact extension of the survivors (seed_filter.cu:762-774)
         k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
-            P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, w->d_hit_bound, w->d_plan,
+            P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, surv_cap, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
             w->d_anchors_a, anchor_cap, w->d_counters, D);
         pt.mark(PH_EXTEND);
         // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the anchors
@@ -379,25 +441,38 @@ int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_
         k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters);
         pt.mark(PH_SORT);
         launches += 2;
-        CU(cudaMemcpyAsync(w->h_small, w->d_counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
-        CU(cudaMemcpyAsync(w->h_small + 8, w->d_plan, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(w->h_small, w->d_counters, CTR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(w->h_small + 16, w->d_plan, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
         CU(cudaMemcpyAsync(w->h_out, w->d_out, FINALIZE_CAP * sizeof(sa_segment), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
         CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-        num_iter = w->h_small[8];
-        num_hits = w->h_small[9];
-        num_seeds = std::min(w->h_small[10], max_items);
         n_pre = w->h_small[CTR_ANCHORS];
-        n_surv = filter ? w->h_small[CTR_SURV] : num_hits;
         memcpy(&ext_cells, &w->h_small[CTR_EXT_LO], 8);
-        if (num_iter == 0xFFFFFFFFu) { // more iterations than the plan arrays hold
-            size_t need = (size_t)num_hits / G.max_hits + 2;
-            TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
-            TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
-            continue;
+        if (fused) {
+            num_hits = w->h_small[CTR_NHITS];
+            num_seeds = w->h_small[CTR_NSEEDS];
+            n_surv = w->h_small[CTR_SURV];
+            if (num_hits >= G.max_hits) { // more than one iteration pair: the general path decides
+                fused = false;
+                continue;
+            }
+        } else {
+            num_iter = w->h_small[16];
+            num_hits = w->h_small[17];
+            num_seeds = std::min(w->h_small[18], max_items);
+            n_surv = filter ? w->h_small[CTR_SURV] : num_hits;
+            if (num_iter == 0xFFFFFFFFu) { // more iterations than the plan arrays hold
+                size_t need = (size_t)num_hits / G.max_hits + 2;
+                TRY(ensure(w->d_limit_pos, w->limit_cap, need, "limit_pos"));
+                TRY(ensure(w->d_hit_bound, w->bound_cap, need, "hit_bound"));
+                continue;
+            }
+            if (num_hits > hits_cap) { // the hit list did not fit: grow and replay
+                TRY(ensure(w->d_hits, w->hits_cap, num_hits, "hsp"));
+                continue;
+            }
         }
-        if (num_hits > hits_cap) { // the hit list did not fit: grow and replay
-            TRY(ensure(w->d_hits, w->hits_cap, num_hits, "hsp"));
-            TRY(ensure(w->d_surv, w->surv_cap, w->hits_cap, "survivors", 1, 1));
+        if (filter && n_surv > surv_cap) { // the survivor list did not fit
+            TRY(ensure(w->d_surv, w->surv_cap, n_surv, "survivors"));
             continue;
         }
         if (n_pre > anchor_cap) { // the anchor list did not fit
@@ -411,7 +486,7 @@ int run_pipeline(Workspace *w, uint32_t max_items, int rev, uint32_t buffer, sa_
             n_final = w->h_small[CTR_OUT];
             staged = true;
         } else {
-            // many anchors (self-alignment, repeat families, long homologous runs): device-wide sorts
+            // many distinct anchors (repeat families, forced small iterations): device-wide sorts
             TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
             TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
             CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
@@ -541,6 +616,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     G.use_filter = !(fenv && atoi(fenv) == 0);
     const char *denv = getenv("SEGALIGN_B200_DEDUP");
     G.use_dedup = !(denv && atoi(denv) == 0);
+    const char *uenv = getenv("SEGALIGN_B200_FUSED");
+    G.use_fused = !(uenv && atoi(uenv) == 0);
     const char *env = getenv("SEGALIGN_B200_STREAMS");
     if (env && atoi(env) > 0) G.ws_per_gpu = atoi(env);
     for (size_t i = 0; i < G.gpus.size(); i++) {
@@ -549,7 +626,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaMalloc((void **)&g.d_sub_mat, 64 * sizeof(int)), SA_ERR_MALLOC);
         CU(cudaMemcpy(g.d_sub_mat, sub_mat, 64 * sizeof(int), cudaMemcpyHostToDevice), SA_ERR_MEMCPY);
         int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_hits, FILTER_THREADS,
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_hits<SRC_RANGE>, FILTER_THREADS,
                                                          FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device), SA_ERR_KERNEL);
         G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
@@ -593,7 +670,7 @@ int sa_set_seed_shape(const char *pattern) {
         if (pattern[i] == '1' || pattern[i] == 'T') {
             sh.pos[sh.weight] = (uint8_t)i;
             sh.trans[sh.weight] = pattern[i] == 'T';
-            sh.num_trans += pattern[i] == 'T';
+            if (pattern[i] == 'T') sh.tvar[sh.num_trans++] = (uint8_t)sh.weight;
             sh.weight++;
         }
     }
@@ -763,10 +840,12 @@ int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint3
     TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
     TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
     CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
-    w->h_small[12] = num_seeds; // pinned: the seed count travels to d_plan[2] on the stream
-    CU(cudaMemcpyAsync(w->d_plan + 2, w->h_small + 12, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    w->h_small[20] = num_seeds; // pinned: the seed count travels to d_plan[2] on the stream
+    CU(cudaMemcpyAsync(w->d_plan + 2, w->h_small + 20, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
     pt.mark(PH_SEEDS);
-    return run_pipeline(w, num_seeds, rev, buffer, out, out_count, nullptr, pt);
+    CallInput in = {};
+    in.src = SRC_SEEDS; in.max_items = num_seeds; in.per = 1; in.transition = G.transition;
+    return run_pipeline(w, in, rev, buffer, out, out_count, nullptr, pt);
 }
 
 int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev,
@@ -796,23 +875,11 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
         printf("MAX_SEEDS exceeded\n");
         return fail(SA_ERR_MAX_SEEDS, "range of %u positions x %u words > MAX_SEEDS %u", n, per, G.max_seeds);
     }
-    const uint32_t max_items = (uint32_t)max_items64;
-    cudaStream_t st = w->stream;
-    TRY(ensure(w->d_flags, w->flags_cap, n, "seed_flags"));
-    TRY(ensure(w->d_excl, w->excl_cap, (size_t)n + 1, "seed_excl"));
-    TRY(ensure(w->d_seeds, w->seeds_cap, max_items, "seed_offsets"));
-    TRY(ensure(w->d_prefix, w->prefix_cap, max_items, "hit_num"));
-    size_t bytes = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
-    TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
-    // seed words of src/seeder.cpp:57-74 on the device; their count stays on the device (d_plan[2])
-    k_seed_flags<<<grid_for(n, 256), 256, 0, st>>>(q.m1, G.shape.span, q_start, q_end, w->d_flags);
-    CU(cub::DeviceScan::ExclusiveSum(w->d_temp, bytes, w->d_flags, w->d_excl, (int)n, st), SA_ERR_KERNEL);
-    k_seed_emit<<<grid_for(n, 256), 256, 0, st>>>(q.p2, w->d_flags, w->d_excl, G.shape, transition, q_start, q_end,
-                                                  w->d_seeds, w->d_plan + 2);
-    add_launches(4);
+    CallInput in = {};
+    in.src = SRC_RANGE; in.max_items = (uint32_t)max_items64;
+    in.q_start = q_start; in.q_end = q_end; in.per = per; in.transition = transition;
     pt.mark(PH_SEEDS);
-    return run_pipeline(w, max_items, rev, buffer, out, out_count, out_num_seeds, pt);
+    return run_pipeline(w, in, rev, buffer, out, out_count, out_num_seeds, pt);
 }
 
 void sa_release_result(sa_segment *out) { free(out); }

@@ -44,6 +44,7 @@ struct ShapeDesc {
     int num_trans;   // number of care positions that allow a transition
     uint8_t pos[32];   // care positions, first = most significant
     uint8_t trans[32]; // transition_pos[t]
+    uint8_t tvar[32];  // tvar[i] = care-position index t of the i-th transition variant (seeder.cpp:64-71)
 };
 
 struct ExtendParams {

@@ -40,6 +40,17 @@ def test_without_duplicate_table_matches_reference_golden(backend, name, monkeyp
     H.assert_calls_equal(got, want, "no duplicate table vs reference golden")
 
 
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("device_seeding", [False, True], ids=["vector", "range"])
+def test_general_path_matches_reference_golden(backend, case, device_seeding, monkeypatch):
+    """SEGALIGN_B200_FUSED=0: hit counts -> scan -> iteration plan -> materialised hit list ->
+    filter -> exact (the path every call with num_hits >= MAX_HITS takes)."""
+    monkeypatch.setenv("SEGALIGN_B200_FUSED", "0")
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=device_seeding)
+    H.assert_calls_equal(got, want, "general path vs reference golden")
+
+
 def test_filter_keeps_a_small_superset(backend):
     """The filter's survivors are few (it is the point of the stage) and contain every HSP."""
     case = H.CASES_BY_NAME["masked_multichrom"]
