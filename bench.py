@@ -137,6 +137,10 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ our arm
+def nthreads_for_env(args, world):
+    return args.host_threads or max(4, min(16, (os.cpu_count() or 4) // max(1, world)))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -145,6 +149,11 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: anything libraries print there (NCCL's version banner)
+    # goes to stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the backend has no CPU fallback")
     torch.cuda.set_device(local)
@@ -163,6 +172,7 @@ def run_ours(args):
     q_rc_ascii = genome.revcomp_ascii(query)
     query_bases = int(query.size)
 
+    os.environ["SEGALIGN_B200_STREAMS"] = str(nthreads_for_env(args, world))
     be = Backend()
     be.InitializeInterface(1, first_device=local)
     be.GenerateShapePos(SEED_SHAPE)
@@ -175,7 +185,9 @@ def run_ours(args):
     be.SendQueryWriteRequest(query, 0, query.size, 0)
     t3 = time.perf_counter()
 
-    nthreads = args.host_threads
+    # host callers (the reference's TBB seeder workers): enough to keep PCIe, the host seeding
+    # loop and the GPU busy at once; one backend workspace (stream) per caller
+    nthreads = args.host_threads or max(4, min(16, (os.cpu_count() or 4) // max(1, world)))
     pool = ThreadPoolExecutor(max_workers=nthreads)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -270,7 +282,10 @@ def run_ours(args):
         peaks = json.loads(pk.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
     n_launch = max(1, st_res["calls"])
-    alg_bytes = 64.0 * st_res["hits"] + st_res["ext_cells"]
+    # the dominant kernel does lookup + expansion + extension filter in one launch (fused path):
+    # B_L + B_X = (16 S + 4 H) + (64 H + E), SURVEY 8d
+    lookup_bytes = 16.0 * st_res["seeds"] + 4.0 * st_res["hits"]
+    alg_bytes = lookup_bytes + 64.0 * st_res["hits"] + st_res["ext_cells"]
     t_ext = st_res["ms_prefilter"] * 1e-3
     achieved = alg_bytes / t_ext / 1e9 if t_ext > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k_filter_hits", "achieved": round(achieved, 1), "peak": peak,
@@ -279,13 +294,11 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
                 "avg_launch_ms": round(st_res["ms_prefilter"] / n_launch, 4), "launches": n_launch,
                 "traffic": None,
-                "lookup": {"kernel": "k_count_hits+scan+k_expand_hits",
-                           "algorithmic_bytes_per_launch": round((16.0 * st_res["seeds"] + 4.0 * st_res["hits"]) / n_launch),
-                           "achieved": round((16.0 * st_res["seeds"] + 4.0 * st_res["hits"]) /
-                                             max(1e-9, (st_res["ms_count_scan"] + st_res["ms_lookup"]) * 1e-3) / 1e9, 1)},
+                "bytes_formula": "16*S + 4*H (seed lookup, fused into this kernel) + 64*H + E (extension), per rank",
+                "lookup": {"fused_into": "k_filter_hits", "algorithmic_bytes_per_launch": round(lookup_bytes / n_launch)},
                 "phase_ms_per_step": {k: round(st_res[k] / args.steps, 3) for k in
                                       ("ms_h2d", "ms_count_scan", "ms_lookup", "ms_prefilter", "ms_extend", "ms_sort", "ms_d2h")},
-                "note": "phase times are summed over concurrent streams (host_threads calls in flight)"}
+                "note": "rank 0; phase times are summed over concurrent streams (host_threads calls in flight)"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -320,7 +333,10 @@ def run_ours(args):
                          "query_upload_encode": round((t3 - t2) * 1e3, 1)},
             "wall_ms_per_step": round(wall_res / args.steps, 3),
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     be.ShutdownProcessor()
     if world > 1:
         dist.barrier()
@@ -441,7 +457,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-mb", type=float, default=None, help="scale the reference block (testing only)")
     ap.add_argument("--query-mb", type=float, default=None, help="truncate the query block (testing only)")
-    ap.add_argument("--host-threads", type=int, default=4)
+    ap.add_argument("--host-threads", type=int, default=0, help="0 = auto: min(16, cores / ranks)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

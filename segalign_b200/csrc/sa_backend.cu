@@ -629,6 +629,14 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_hits<SRC_RANGE>, FILTER_THREADS,
                                                          FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device), SA_ERR_KERNEL);
+        // tuning knobs (experiments): resident filter CTAs per SM and the shared-memory carve-out
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_CARVEOUT")) {
+            int pct = atoi(e);
+            cudaFuncSetAttribute(k_filter_hits<SRC_RANGE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_filter_hits<SRC_SEEDS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_filter_hits<SRC_HITS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
         G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
         G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
         // blocks uploaded before the matrix was known carry records built for another terminator set
