@@ -120,6 +120,21 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
 size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uint32_t j1,
                            int transition, uint64_t *out);
 
+/* Segments writer -- the record formatting of src/segment_printer.cpp:72-94 (plus)
+ * and :125-149 (minus): block-relative HSPs -> "name1 start1 end1 name2 start2 end2 strand score",
+ * origin-one closed, the wire format LASTZ reads with --segments.  chroms: the chromosomes of the
+ * block in block order (r_chr_* / q_chr_* of src/store.h:9-20; for minus != 0 the rc_q_chr_* table);
+ * starts are buffer offsets like r_block_start / q_block_start.  Minus-strand records are written in
+ * reverse order, as the reference does.  Host only (no CUDA). */
+typedef struct sa_chrom_table {
+    const char *const *names;
+    const uint64_t *starts;
+    const uint32_t *lens;
+    uint32_t count;
+} sa_chrom_table;
+int sa_write_segments(const char *path, const sa_segment *hsps, uint32_t n, int minus, uint64_t r_block_start,
+                      uint64_t q_block_start, const sa_chrom_table *ref_chroms, const sa_chrom_table *query_chroms);
+
 /* ShutdownProcessor -- src/seed_filter.cu:932-940 */
 int sa_shutdown_processor(void);
 

@@ -22,7 +22,7 @@ ABI_SYMBOLS = [
     "sa_send_ref", "sa_generate_seed_pos_table", "sa_clear_ref", "sa_send_query",
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
-    "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds",
+    "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds", "sa_write_segments",
 ]
 
 
@@ -36,6 +36,21 @@ class SaStats(C.Structure):
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SaChromTable(C.Structure):
+    _fields_ = [("names", C.POINTER(C.c_char_p)), ("starts", C.POINTER(C.c_uint64)),
+                ("lens", C.POINTER(C.c_uint32)), ("count", C.c_uint32)]
+
+    @classmethod
+    def build(cls, names, starts, lens):
+        n = len(names)
+        t = cls()
+        t._names = (C.c_char_p * n)(*[s.encode() for s in names])
+        t._starts = (C.c_uint64 * n)(*[int(x) for x in starts])
+        t._lens = (C.c_uint32 * n)(*[int(x) for x in lens])
+        t.names, t.starts, t.lens, t.count = t._names, t._starts, t._lens, n
+        return t
 
 
 class BackendError(RuntimeError):
@@ -77,6 +92,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_set_profiling.argtypes = [C.c_int]
     lib.sa_host_chunk_seeds.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     lib.sa_host_chunk_seeds.restype = C.c_size_t
+    lib.sa_write_segments.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64,
+                                      C.POINTER(SaChromTable), C.POINTER(SaChromTable)]
     return lib
 
 
@@ -174,6 +191,14 @@ class Backend:
         self._check(self.lib.sa_seed_and_filter(seeds_ptr, num_seeds, int(rev), buffer,
                                                 C.byref(out), C.byref(n)))
         return self._take(out, n)
+
+    def write_segments(self, path, hsps: np.ndarray, minus: bool, r_block_start: int, q_block_start: int,
+                       ref_chroms: "SaChromTable", query_chroms: "SaChromTable") -> None:
+        """src/segment_printer.cpp:72-94 / :125-149 (host only; works without a GPU)."""
+        hsps = np.ascontiguousarray(hsps, dtype=SEGMENT_DTYPE)
+        self._check(self.lib.sa_write_segments(str(path).encode(), hsps.ctypes.data, hsps.size, int(minus),
+                                               r_block_start, q_block_start, C.byref(ref_chroms),
+                                               C.byref(query_chroms)))
 
     def ShutdownProcessor(self) -> None:
         self._check(self.lib.sa_shutdown_processor())

@@ -355,7 +355,9 @@ k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Surv
             const bool done = dropped || n_eff < 32;
             if (t >= 32u) ext_cells += 32;
             bool emit = false;
-            if (survive) {
+            // M only grows: once the bound reaches hspthresh the hit is a survivor whatever follows, so
+            // the (possibly very long) rest of a homologous run is left to the exact kernel alone
+            if (survive || (left ? right_score : 0) + M >= P.hspthresh) {
                 emit = true;
                 active = false;
             } else if (done) {

@@ -981,4 +981,6 @@ size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uin
     return n;
 }
 
+#include "host_segments.inc"
+
 } // extern "C"

@@ -149,3 +149,21 @@ def chunk_seeds(seq: np.ndarray, j0: int, j1: int, pattern: str, transition: boo
             if trans[t]:
                 cols.append(((kmer ^ (np.uint64(2) << np.uint64(2 * t))) << np.uint64(32)) + js)
     return np.stack(cols, axis=1).reshape(-1)
+
+
+def block_tables(block: np.ndarray, prefix: str, block_start: int = 0):
+    """Chromosome tables of one block as src/main.cpp keeps them: (names, starts, lens) in block
+    order (q_chr_* / r_chr_*, main.cpp:341-344) and for the reverse-complement block
+    (rc_q_chr_*, main.cpp:365-370: chromosomes in reverse order, start = 2*block_start + block_len
+    - start - len).  Chromosomes are the '&'-separated pieces of the block."""
+    amp = np.flatnonzero(block == ord("&"))
+    starts = np.concatenate([[0], amp + 1]).astype(np.int64) + block_start
+    ends = np.concatenate([amp, [block.size]]).astype(np.int64) + block_start
+    lens = ends - starts
+    names = [f"{prefix}{i}" for i in range(starts.size)]
+    fwd = (names, starts.tolist(), lens.tolist())
+    order = range(starts.size - 1, -1, -1)
+    rc = ([names[i] for i in order],
+          [int(2 * block_start + block.size - starts[i] - lens[i]) for i in order],
+          [int(lens[i]) for i in order])
+    return fwd, rc
