@@ -180,7 +180,7 @@ k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Surv
     bool active = false, left = false;
     uint32_t key = 0, r0 = 0, q0 = 0, t = 0;
     int s = 0, M = 0, right_score = 0;
-    unsigned long long ext_cells = 0;
+    uint32_t ext_tiles = 0; // tiles walked beyond the first one of a direction (32-bit: stays in a register)
 
     for (;;) {
         const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
@@ -353,7 +353,7 @@ k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Surv
                 }
             }
             const bool done = dropped || n_eff < 32;
-            if (t >= 32u) ext_cells += 32;
+            ext_tiles += t >= 32u ? 1u : 0u;
             bool emit = false;
             // M only grows: once the bound reaches hspthresh the hit is a survivor whatever follows, so
             // the (possibly very long) rest of a homologous run is left to the exact kernel alone
@@ -377,9 +377,353 @@ k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Surv
             }
         }
     }
-    if (ext_cells) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), ext_cells);
+    if (ext_tiles) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), 32ull * ext_tiles);
     if (SRC != SRC_HITS && lane == 0) {
         if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits); // uint32 wrap-around like the reference's scan
+        if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
+        if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Two-phase variant of the filter kernel (the default).
+//
+// Profiling the persistent-lane kernel above showed ~240 of its ~420 instructions per 32-cell trip
+// outside the eight 4-cell groups: per-trip window loads and assembly, the per-lane walk state
+// machine and its share of work staging -- paid 2.9 times per hit -- plus one exposed L2 latency
+// per trip.  Almost every hit needs exactly: right tile 0, left tile 0, and usually left tile 1.
+//   phase 1  a warp takes 32 fresh hits, one per lane, loads the 4+4 records that cover
+//            [r0-64, r0+32) / [q0-64, q0+32) with eight independent 16-byte loads, and walks
+//            right 0, left 0, left 1 as straight-line code: no state machine, no per-tile loads,
+//            all lanes in the same tile.  ~70 % of the hits are decided here.
+//   phase 2  hits whose walk is still open (right beyond 32 cells, left beyond 64) go to a per-warp
+//            continuation queue in shared memory with their walk state; when the queue holds
+//            CQ_DRAIN entries (or no fresh hits are left) the warp drains it with the persistent-
+//            lane loop of the kernel above.
+// Decisions and bounds are exactly those of k_filter_hits (same tile walk, same survivor rule).
+constexpr int CQ_CAP = 96;   // continuation queue entries per warp
+constexpr int CQ_DRAIN = 64; // drain when at least this many are queued
+
+struct Cont {
+    uint32_t r0, q0, key, t;   // t = cells already walked in the open direction
+    int s, M, right_score;
+    uint32_t left;
+};
+
+// 32 cells from two adjacent records at cell offset sh (0..31) of the first
+__device__ __forceinline__ void assemble_window(const uint4 a, const uint4 b, uint32_t sh, uint64_t &R,
+                                                uint32_t &T, uint32_t &S) {
+    const bool lo = sh < 16u;
+    const uint32_t w0 = lo ? a.x : a.y, w1 = lo ? a.y : b.x, w2 = lo ? b.x : b.y;
+    const uint32_t k = (2u * sh) & 31u;
+    R = ((uint64_t)__funnelshift_r(w1, w2, k) << 32) | __funnelshift_r(w0, w1, k);
+    T = __funnelshift_r(a.z, b.z, sh);
+    S = __funnelshift_r(a.w, b.w, sh);
+}
+
+// Walk of one 32-cell window (cells in ascending address order in R/Q/T/S; `left` walks it from the
+// top down).  Updates the running sum s and running max M; done = the walk of this direction ends
+// in this tile; survive = a soft cell lies in the walked range (the exact kernel must decide).
+__device__ __forceinline__ void tile_walk(uint32_t lut_lane, uint32_t mul, uint32_t m4, const int *diag,
+                                          const FilterParams &P, uint64_t R, uint64_t Q, uint32_t T, uint32_t S,
+                                          bool left, int &s, int &M, bool &done, bool &survive) {
+    uint32_t rl = (uint32_t)R, rh = (uint32_t)(R >> 32), ql = (uint32_t)Q, qh = (uint32_t)(Q >> 32);
+    uint32_t m1 = 0x00000001u, m2 = 0x00000101u, m3 = 0x00010101u; // dp4a prefix selectors, processing order
+    if (left) {
+        // descending cells: reverse the BYTES (groups); inside a group the selectors take the order
+        const uint32_t a = __byte_perm(rh, 0, 0x0123), b = __byte_perm(rl, 0, 0x0123);
+        const uint32_t c = __byte_perm(qh, 0, 0x0123), d = __byte_perm(ql, 0, 0x0123);
+        rl = a; rh = b; ql = c; qh = d;
+        T = __brev(T); S = __brev(S);
+        m1 = 0x01000000u; m2 = 0x01010000u; m3 = 0x01010100u;
+    }
+    const int n_eff = __clz(__brev(T));          // cells before the first terminator (32 if none)
+    const uint32_t valid = n_eff >= 32 ? 0xFFFFFFFFu : ((1u << n_eff) - 1u);
+    survive = (S & valid) != 0;
+    const int ng = survive ? 0 : (n_eff + 3) >> 2; // groups to visit (the last may run past the terminator)
+    bool dropped = false;
+    const int X = P.xdrop;
+    if (n_eff == 32 && !survive && rl == ql && rh == qh && P.diag_all_positive) {
+        s += diag_sum32_f(R, diag);               // all-match tile: strictly increasing prefix
+        M = max(M, s);
+    } else {
+        uint32_t sc[8];
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const uint32_t y = g < 4 ? __byte_perm(rl, ql, 0x0040 | (g & 3) << 8 | (4 + (g & 3)))
+                                     : __byte_perm(rh, qh, 0x0040 | (g & 3) << 8 | (4 + (g & 3)));
+            const uint32_t v = group_scores(lut_lane, mul, y);
+            sc[g] = g < ng ? v : 0u;
+        }
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const int p1 = __dp4a((int)sc[g], (int)m1, s);
+            const int p2 = __dp4a((int)sc[g], (int)m2, s);
+            const int p3 = __dp4a((int)sc[g], (int)m3, s);
+            const int p4 = __dp4a((int)sc[g], (int)m4, s);
+            const int mn = min(__vimin3_s32(p1, p2, p3), p4);
+            dropped |= mn < M - X;
+            M = __vimax3_s32(__vimax3_s32(p1, p2, p3), p4, M);
+            s = p4;
+        }
+    }
+    done = dropped || n_eff < 32;
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(FILTER_THREADS, 4)
+k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, SurvRec *__restrict__ surv,
+               uint32_t surv_cap, uint32_t *__restrict__ counters) {
+    extern __shared__ uint32_t lut[];
+    __shared__ int diag[4];
+    for (int i = threadIdx.x; i < FILTER_LUT_WORDS; i += blockDim.x) {
+        const int idx = i >> 4, rn = idx >> 4, qn = idx & 15;
+        const int s0 = sub_mat[(rn & 3) * 8 + (qn & 3)], s1 = sub_mat[(rn >> 2) * 8 + (qn >> 2)];
+        lut[i] = (uint32_t)(uint8_t)(int8_t)s0 | ((uint32_t)(uint8_t)(int8_t)s1 << 8);
+    }
+    if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + (lane & 15u) * 4u;
+    const uint32_t mul = P.k_mul, m4 = P.k_m4;
+    const int thr = P.hspthresh;
+
+    __shared__ uint2 hitbuf[FILTER_THREADS / 32][FILTER_CHUNK];
+    __shared__ uint8_t ownbuf[FILTER_THREADS / 32][FILTER_CHUNK];
+    __shared__ uint4 contq[FILTER_THREADS / 32][CQ_CAP][2];
+    uint2 *mybuf = hitbuf[threadIdx.x >> 5];
+    uint8_t *myown = ownbuf[threadIdx.x >> 5];
+    uint4(*myq)[2] = contq[threadIdx.x >> 5];
+    const uint32_t total_items = SRC == SRC_HITS ? min(H.plan[1], H.hits_cap) : H.num_items;
+    uint32_t key_base = 0, cursor = 0, limit = 0, g_total = 0, g_done = 0; // as in k_filter_hits
+    bool exhausted = false;
+    uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0;
+    bool any_hits = false;
+    uint32_t qcount = 0; // warp-uniform: queued continuations
+    uint32_t ext_tiles = 0;
+
+    auto emit = [&](uint32_t r0, uint32_t q0, uint32_t key) {
+        const uint32_t slot = atomicAdd(counters + CTR_SURV, 1u);
+        if (slot < surv_cap) { SurvRec rec; rec.r0 = r0; rec.q0 = q0; rec.key = key; surv[slot] = rec; }
+    };
+
+    for (;;) {
+        // ---------------- stage the next chunk of fresh hits (identical to k_filter_hits)
+        while (cursor == limit && !exhausted) {
+            if (SRC == SRC_HITS) {
+                uint32_t c = 0;
+                if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
+                c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                const unsigned long long start = (unsigned long long)c * FILTER_CHUNK;
+                key_base = start < total_items ? (uint32_t)start : total_items;
+                const uint32_t cnt = min(total_items - key_base, FILTER_CHUNK);
+                exhausted = cnt == 0;
+                __syncwarp();
+#pragma unroll
+                for (uint32_t k = 0; k < FILTER_CHUNK / 32; k++)
+                    if (k * 32u + lane < cnt) mybuf[k * 32u + lane] = __ldg(H.hits + key_base + k * 32u + lane);
+                __syncwarp();
+                cursor = 0; limit = cnt;
+            } else {
+                if (g_done == g_total) { // next group of 32 seed words
+                    uint32_t c = 0;
+                    if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
+                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                    const unsigned long long start = (unsigned long long)c * 32u;
+                    if (start >= total_items) { exhausted = true; break; }
+                    key_base = (uint32_t)start;
+                    g_done = 0;
+                    g_total = 0xFFFFFFFFu;
+                }
+                const uint32_t k = key_base + lane;
+                uint32_t b_start = 0, n = 0, qa = 0;
+                bool valid = false;
+                if (k < total_items) {
+                    uint32_t kmer = 0, qpos = 0;
+                    if (SRC == SRC_SEEDS) {
+                        const uint64_t word = __ldg(H.seeds + k);
+                        kmer = (uint32_t)(word >> 32); qpos = (uint32_t)word;
+                        valid = true;
+                    } else {
+                        const uint32_t pi = k / H.per, v = k - pi * H.per;
+                        qpos = H.j0 + pi;
+                        uint64_t W; uint32_t Tw, Sw;
+                        load_window(P.qrec, (int)qpos, W, Tw, Sw);
+                        const uint32_t span_mask = H.shape.span >= 32 ? 0xFFFFFFFFu : ((1u << H.shape.span) - 1u);
+                        valid = ((Tw | Sw) & span_mask) == 0;
+                        for (int i = 0; i < H.shape.weight; i++) kmer = (kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
+                        if (v > 0) kmer ^= 2u << (2 * H.shape.tvar[v - 1]);
+                    }
+                    if (valid) {
+                        const uint32_t b_end = __ldg(H.index_table + kmer);
+                        b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                        n = b_end - b_start;
+                        qa = qpos + H.seed_size;
+                    }
+                }
+                uint32_t incl = n;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                    if (lane >= (uint32_t)off) incl += up;
+                }
+                const uint32_t excl = incl - n;
+                if (g_total == 0xFFFFFFFFu) {
+                    g_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                    acc_hits += g_total;
+                    acc_seeds += __popc(__ballot_sync(0xFFFFFFFFu, valid));
+                    const unsigned with_hits = __ballot_sync(0xFFFFFFFFu, n > 0);
+                    if (with_hits) { acc_last = key_base + (31u - __clz(with_hits)); any_hits = true; }
+                    if (g_total == 0) continue;
+                }
+                const uint32_t cnt = min(g_total - g_done, FILTER_CHUNK);
+                __syncwarp();
+#pragma unroll
+                for (uint32_t kk = 0; kk < FILTER_CHUNK / 32; kk++) {
+                    const uint32_t f = g_done + kk * 32u + lane;
+                    uint32_t lo = 0, hi = 31;
+#pragma unroll
+                    for (int it = 0; it < 5; it++) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        const uint32_t vmid = __shfl_sync(0xFFFFFFFFu, incl, mid);
+                        if (vmid > f) hi = mid; else lo = mid + 1;
+                    }
+                    const uint32_t o_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
+                    const uint32_t o_start = __shfl_sync(0xFFFFFFFFu, b_start, lo);
+                    const uint32_t o_q = __shfl_sync(0xFFFFFFFFu, qa, lo);
+                    if (kk * 32u + lane < cnt) {
+                        const uint32_t r = __ldg(H.pos_table + o_start + (f - o_excl)) + H.seed_size;
+                        mybuf[kk * 32u + lane] = make_uint2(r, o_q);
+                        myown[kk * 32u + lane] = (uint8_t)lo;
+                    }
+                }
+                __syncwarp();
+                g_done += cnt;
+                cursor = 0; limit = cnt;
+            }
+        }
+        const bool fresh = cursor < limit;
+        if (!fresh && qcount == 0) break; // exhausted and nothing queued
+
+        // ---------------- phase 1: 32 fresh hits, straight-line right 0 / left 0 / left 1
+        if (fresh) {
+            const uint32_t n1 = min(limit - cursor, 32u);
+            const bool have = lane < n1;
+            uint32_t r0 = 0, q0 = 0, key = 0;
+            if (have) {
+                const uint32_t slot = cursor + lane;
+                const uint2 hit = mybuf[slot];
+                r0 = hit.x; q0 = hit.y;
+                key = key_base + (SRC == SRC_HITS ? slot : (uint32_t)myown[slot]);
+            }
+            cursor += n1;
+            // records w0-2 .. w0+1 cover [r0-64, r0+32); the three windows share the cell offset r0 & 31
+            const int wr = (int)(r0 >> 5), wq = (int)(q0 >> 5);
+            const uint32_t shr = r0 & 31u, shq = q0 & 31u;
+            const uint4 rr0 = __ldg(P.rrec + wr - 2), rr1 = __ldg(P.rrec + wr - 1), rr2 = __ldg(P.rrec + wr), rr3 = __ldg(P.rrec + wr + 1);
+            const uint4 qq0 = __ldg(P.qrec + wq - 2), qq1 = __ldg(P.qrec + wq - 1), qq2 = __ldg(P.qrec + wq), qq3 = __ldg(P.qrec + wq + 1);
+            uint64_t R, Q;
+            uint32_t Tr, Tq, Sr, Sq;
+            int s = 0, M = 0, right_score = 0;
+            bool done = false, survive = false;
+            bool open = have;        // this lane's hit is still undecided inside phase 1
+            bool push = false;       // ... and goes to the continuation queue
+            uint32_t c_t = 0, c_left = 0;
+            // right tile 0: cells r0 .. r0+31
+            assemble_window(rr2, rr3, shr, R, Tr, Sr);
+            assemble_window(qq2, qq3, shq, Q, Tq, Sq);
+            tile_walk(lut_lane, mul, m4, diag, P, R, Q, Tr | Tq, Sr | Sq, false, s, M, done, survive);
+            if (open) {
+                if (survive || M >= thr) { emit(r0, q0, key); open = false; }
+                else if (!done) { push = true; c_t = 32; c_left = 0; open = false; }
+                else right_score = M;
+            }
+            int cs = s, cM = M; // state of a pushed right walk
+            // left tile 0: cells r0-32 .. r0-1, walked downwards
+            if (__any_sync(0xFFFFFFFFu, open)) {
+                s = 0; M = 0;
+                assemble_window(rr1, rr2, shr, R, Tr, Sr);
+                assemble_window(qq1, qq2, shq, Q, Tq, Sq);
+                tile_walk(lut_lane, mul, m4, diag, P, R, Q, Tr | Tq, Sr | Sq, true, s, M, done, survive);
+                if (open) {
+                    if (survive || right_score + M >= thr) { emit(r0, q0, key); open = false; }
+                    else if (done) open = false; // decided: not an HSP
+                }
+                // left tile 1: cells r0-64 .. r0-33
+                if (__any_sync(0xFFFFFFFFu, open)) {
+                    assemble_window(rr0, rr1, shr, R, Tr, Sr);
+                    assemble_window(qq0, qq1, shq, Q, Tq, Sq);
+                    tile_walk(lut_lane, mul, m4, diag, P, R, Q, Tr | Tq, Sr | Sq, true, s, M, done, survive);
+                    if (open) {
+                        ext_tiles++;
+                        if (survive || right_score + M >= thr) emit(r0, q0, key);
+                        else if (!done) { push = true; c_t = 64; c_left = 1; cs = s; cM = M; }
+                        open = false;
+                    }
+                }
+            }
+            // queue the open walks (ballot compaction; CQ_CAP - CQ_DRAIN >= 32 guarantees room)
+            const unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
+            if (push) {
+                const uint32_t idx = qcount + __popc(pm & lt_mask);
+                myq[idx][0] = make_uint4(r0, q0, key, c_t);
+                myq[idx][1] = make_uint4((uint32_t)cs, (uint32_t)cM, (uint32_t)right_score, c_left);
+            }
+            qcount += __popc(pm);
+            __syncwarp();
+        }
+
+        // ---------------- phase 2: drain the continuation queue with persistent lanes
+        if (qcount >= (uint32_t)CQ_DRAIN || (qcount > 0 && cursor == limit && exhausted)) {
+            uint32_t qhead = 0;
+            bool active = false, left = false;
+            uint32_t key = 0, r0 = 0, q0 = 0, t = 0;
+            int s = 0, M = 0, right_score = 0;
+            for (;;) {
+                const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
+                if (need && qhead < qcount) {
+                    const uint32_t avail = qcount - qhead;
+                    const uint32_t rank = __popc(need & lt_mask);
+                    if (!active && rank < avail) {
+                        const uint4 a = myq[qhead + rank][0], b = myq[qhead + rank][1];
+                        r0 = a.x; q0 = a.y; key = a.z; t = a.w;
+                        s = (int)b.x; M = (int)b.y; right_score = (int)b.z; left = b.w != 0;
+                        active = true;
+                    }
+                    const uint32_t nneed = __popc(need);
+                    qhead += nneed < avail ? nneed : avail;
+                }
+                if (!__any_sync(0xFFFFFFFFu, active)) break;
+                if (active) {
+                    const int cr = left ? (int)r0 - (int)t - 32 : (int)r0 + (int)t;
+                    const int cq = left ? (int)q0 - (int)t - 32 : (int)q0 + (int)t;
+                    uint64_t R, Q;
+                    uint32_t Tr, Tq, Sr, Sq;
+                    load_window(P.rrec, cr, R, Tr, Sr);
+                    load_window(P.qrec, cq, Q, Tq, Sq);
+                    bool done, survive;
+                    tile_walk(lut_lane, mul, m4, diag, P, R, Q, Tr | Tq, Sr | Sq, left, s, M, done, survive);
+                    ext_tiles += t >= 32u ? 1u : 0u;
+                    if (survive || (left ? right_score : 0) + M >= thr) {
+                        emit(r0, q0, key);
+                        active = false;
+                    } else if (done) {
+                        if (!left) { right_score = M; left = true; t = 0; s = 0; M = 0; }
+                        else active = false;
+                    } else {
+                        t += 32u;
+                    }
+                }
+            }
+            qcount = 0;
+            __syncwarp();
+        }
+    }
+    if (ext_tiles) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), 32ull * ext_tiles);
+    if (SRC != SRC_HITS && lane == 0) {
+        if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits);
         if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
         if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
     }

@@ -131,6 +131,8 @@ struct Global {
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
     bool use_fused = true;     // SEGALIGN_B200_FUSED=0 always takes the general (materialised hit list) path
     int filter_grid = 0;
+    int filter2_grid = 0;      // two-phase filter kernel (k_filter_hits2), the default
+    int filter_kernel = 2;     // SEGALIGN_B200_FILTER_KERNEL=1 selects the single-phase kernel
     int extend_grid = 0;
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
@@ -393,10 +395,17 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         }
         if (fused) {
             H.seeds = w->d_seeds;
-            if (in.src == SRC_SEEDS)
-                k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
-            else
-                k_filter_hits<SRC_RANGE><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+            if (G.filter_kernel == 1) {
+                if (in.src == SRC_SEEDS)
+                    k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                else
+                    k_filter_hits<SRC_RANGE><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+            } else {
+                if (in.src == SRC_SEEDS)
+                    k_filter_hits2<SRC_SEEDS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                else
+                    k_filter_hits2<SRC_RANGE><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+            }
             launches++;
             pt.mark(PH_FILTER);
         } else {
@@ -426,7 +435,10 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             // 4a. stage A: conservative score bound over all hits -> survivor records
             if (filter) {
                 H.hits = w->d_hits; H.hits_cap = hits_cap;
-                k_filter_hits<SRC_HITS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                if (G.filter_kernel == 1)
+                    k_filter_hits<SRC_HITS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                else
+                    k_filter_hits2<SRC_HITS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 launches++;
                 pt.mark(PH_FILTER);
             }
@@ -638,6 +650,12 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
             cudaFuncSetAttribute(k_filter_hits<SRC_HITS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }
         G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
+        int per_sm2 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_filter_hits2<SRC_RANGE>, FILTER_THREADS,
+                                                         FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm2 = std::min(per_sm2, atoi(e));
+        G.filter2_grid = std::max(1, per_sm2) * std::max(1, sms);
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) G.filter_kernel = atoi(e) == 1 ? 1 : 2;
         G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
