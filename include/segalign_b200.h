@@ -157,6 +157,7 @@ typedef struct sa_stats {
     double ms_h2d, ms_count_scan, ms_lookup, ms_prefilter, ms_extend, ms_sort, ms_d2h;
     double ms_ref_encode, ms_table_build, ms_query_encode;
     uint64_t launches;         /* kernels launched by this library */
+    uint64_t walked;           /* hits the popcount screen left to the tile walk (0 for the tile-walk-only kernels) */
 } sa_stats;
 int sa_get_stats(sa_stats *out);
 int sa_reset_stats(void);

@@ -41,7 +41,7 @@ def _newer(target: Path, sources) -> bool:
 
 
 def build_backend(force: bool = False, verbose: bool = False) -> Path:
-    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "segalign_b200.h"]
+    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.inc")) + [ROOT / "include" / "segalign_b200.h"]
     if not force and _newer(LIB, sources):
         return LIB
     cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "sa_backend.cu")]

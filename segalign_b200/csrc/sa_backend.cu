@@ -24,6 +24,7 @@
 #include "kernels_extend.cuh"
 #include "kernels_filter.cuh"
 #include "kernels_lookup.cuh"
+#include "kernels_screen.cuh"
 #include "kernels_sort.cuh"
 #include "sa_common.cuh"
 
@@ -131,8 +132,10 @@ struct Global {
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
     bool use_fused = true;     // SEGALIGN_B200_FUSED=0 always takes the general (materialised hit list) path
     int filter_grid = 0;
-    int filter2_grid = 0;      // two-phase filter kernel (k_filter_hits2), the default
-    int filter_kernel = 2;     // SEGALIGN_B200_FILTER_KERNEL=1 selects the single-phase kernel
+    int filter2_grid = 0;      // two-phase tile-walk kernel (k_filter_hits2)
+    int filter3_grid = 0;      // popcount screen + tile walk (k_filter_hits3), the default on the fused path
+    int filter_kernel = 3;     // SEGALIGN_B200_FILTER_KERNEL=1|2 select the single-phase / two-phase tile-walk kernels
+    ScreenConsts screen = {};  // class scores of the popcount screen (screen_bound.h)
     int extend_grid = 0;
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
@@ -350,7 +353,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     GpuCtx &g = G.gpus[w->gpu];
     cudaStream_t st = w->stream;
     uint64_t launches = 0;
-    uint32_t num_hits = 0, num_iter = 0, num_seeds = 0, n_pre = 0, n_final = 0, n_surv = 0;
+    uint32_t num_hits = 0, num_iter = 0, num_seeds = 0, n_pre = 0, n_final = 0, n_surv = 0, n_walked = 0;
     unsigned long long ext_cells = 0;
     const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
     const bool filter = G.filter_ok && G.use_filter;
@@ -395,7 +398,12 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         }
         if (fused) {
             H.seeds = w->d_seeds;
-            if (G.filter_kernel == 1) {
+            if (G.filter_kernel == 3 && G.screen.enabled) {
+                if (in.src == SRC_SEEDS)
+                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                else
+                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+            } else if (G.filter_kernel == 1) {
                 if (in.src == SRC_SEEDS)
                     k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 else
@@ -463,6 +471,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             num_hits = w->h_small[CTR_NHITS];
             num_seeds = w->h_small[CTR_NSEEDS];
             n_surv = w->h_small[CTR_SURV];
+            n_walked = w->h_small[CTR_WALKED];
             if (num_hits >= G.max_hits) { // more than one iteration pair: the general path decides
                 fused = false;
                 continue;
@@ -543,6 +552,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         s.calls++; s.seeds += num_seeds; s.hits += num_hits; s.survivors += n_surv;
         s.anchors_pre_dedupe += n_pre; s.hsps += n_final; s.ext_cells += ext_cells;
         s.launches += launches;
+        s.walked += n_walked;
         if (pt.on) {
             s.ms_h2d += pt.ms(PH_SEEDS);
             s.ms_count_scan += pt.ms(PH_PLAN);
@@ -617,6 +627,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++)
             if (sub_mat[a * 8 + b] < -128 || sub_mat[a * 8 + b] > 127) G.filter_ok = false;
+    G.screen = screen_consts_from_matrix(sub_mat, xdrop, hspthresh);
+    if (!G.filter_ok) G.screen.enabled = 0;
     G.term_codes = 0;
     for (int c = 4; c < 8; c++) {
         bool term = true;
@@ -655,7 +667,14 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
                                                          FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
         if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm2 = std::min(per_sm2, atoi(e));
         G.filter2_grid = std::max(1, per_sm2) * std::max(1, sms);
-        if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) G.filter_kernel = atoi(e) == 1 ? 1 : 2;
+        CU(cudaFuncSetAttribute(k_filter_hits3<SRC_RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCR_SMEM_BYTES), SA_ERR_KERNEL);
+        CU(cudaFuncSetAttribute(k_filter_hits3<SRC_SEEDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCR_SMEM_BYTES), SA_ERR_KERNEL);
+        int per_sm3 = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_filter_hits3<SRC_RANGE>, FILTER_THREADS, SCR_SMEM_BYTES), SA_ERR_KERNEL);
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm3 = std::min(per_sm3, atoi(e));
+        G.filter3_grid = std::max(1, per_sm3) * std::max(1, sms);
+        G.filter_kernel = 3;
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) { int v = atoi(e); if (v >= 1 && v <= 3) G.filter_kernel = v; }
         G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};

@@ -51,6 +51,31 @@ def test_general_path_matches_reference_golden(backend, case, device_seeding, mo
     H.assert_calls_equal(got, want, "general path vs reference golden")
 
 
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("kernel", ["1", "2"], ids=["single_phase", "two_phase"])
+@pytest.mark.parametrize("device_seeding", [False, True], ids=["vector", "range"])
+def test_tile_walk_kernels_match_reference_golden(backend, case, kernel, device_seeding, monkeypatch):
+    """SEGALIGN_B200_FILTER_KERNEL=1|2: the tile-walk-only filter kernels (no popcount screen) that
+    the default kernel (3) falls back to for matrices the screen does not admit."""
+    monkeypatch.setenv("SEGALIGN_B200_FILTER_KERNEL", kernel)
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=device_seeding)
+    H.assert_calls_equal(got, want, f"filter kernel {kernel} vs reference golden")
+
+
+def test_screen_decides_most_random_hits(backend):
+    """The popcount screen (default kernel) must be live -- few hits reach the tile walk on a
+    diverged random pair -- and the tile-walk-only kernel must report none."""
+    case = H.CASES_BY_NAME["random_pair"]
+    ref, query = case.inputs()
+    backend.reset_stats()
+    H.run_backend(backend, case, ref, query, device_seeding=True)
+    st = backend.stats()
+    assert st["hits"] > 1000
+    assert 0 < st["walked"] < 0.15 * st["hits"], st
+    assert st["survivors"] <= st["walked"]
+
+
 def test_filter_keeps_a_small_superset(backend):
     """The filter's survivors are few (it is the point of the stage) and contain every HSP."""
     case = H.CASES_BY_NAME["masked_multichrom"]
