@@ -18,7 +18,7 @@ SEGMENT_DTYPE = np.dtype([("ref_start", "<u4"), ("query_start", "<u4"), ("len", 
 # every symbol include/segalign_b200.h declares
 ABI_SYMBOLS = [
     "sa_last_error", "sa_initialize_interface", "sa_initialize_interface_at",
-    "sa_initialize_processor", "sa_set_max_hits", "sa_get_max_hits", "sa_set_seed_shape",
+    "sa_initialize_processor", "sa_set_max_hits", "sa_get_max_hits", "sa_set_filter_kernel", "sa_set_seed_shape",
     "sa_send_ref", "sa_generate_seed_pos_table", "sa_clear_ref", "sa_send_query",
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
@@ -74,6 +74,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_initialize_processor.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_int),
                                             C.c_int, C.c_int, C.c_int]
     lib.sa_set_max_hits.argtypes = [C.c_uint32]
+    lib.sa_set_filter_kernel.argtypes = [C.c_int]
     lib.sa_set_seed_shape.argtypes = [C.c_char_p]
     lib.sa_send_ref.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     lib.sa_generate_seed_pos_table.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
@@ -209,6 +210,9 @@ class Backend:
 
     def get_max_hits(self) -> int:
         return self.lib.sa_get_max_hits()
+
+    def set_filter_kernel(self, k: int) -> int:
+        return self.lib.sa_set_filter_kernel(int(k))
 
     def get_table(self):
         isz, npos = C.c_uint32(), C.c_uint32()

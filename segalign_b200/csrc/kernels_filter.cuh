@@ -402,8 +402,8 @@ k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Surv
 //            CQ_DRAIN entries (or no fresh hits are left) the warp drains it with the persistent-
 //            lane loop of the kernel above.
 // Decisions and bounds are exactly those of k_filter_hits (same tile walk, same survivor rule).
-constexpr int CQ_CAP = 96;   // continuation queue entries per warp
-constexpr int CQ_DRAIN = 64; // drain when at least this many are queued
+constexpr int CQ_CAP = 64;   // continuation queue entries per warp (static + dynamic shared memory <= 48 KB)
+constexpr int CQ_DRAIN = 32; // drain when at least this many are queued
 
 struct Cont {
     uint32_t r0, q0, key, t;   // t = cells already walked in the open direction

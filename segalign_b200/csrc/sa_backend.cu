@@ -399,10 +399,12 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         if (fused) {
             H.seeds = w->d_seeds;
             if (G.filter_kernel == 3 && G.screen.enabled) {
+                FilterParams F3 = F;
+                F3.k_mul = SCR_K_MUL;
                 if (in.src == SRC_SEEDS)
-                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 else
-                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
             } else if (G.filter_kernel == 1) {
                 if (in.src == SRC_SEEDS)
                     k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
@@ -704,6 +706,11 @@ int sa_set_max_hits(uint32_t max_hits) {
     return SA_OK;
 }
 uint32_t sa_get_max_hits(void) { return G.max_hits; }
+int sa_set_filter_kernel(int kernel) {
+    const int prev = G.filter_kernel;
+    G.filter_kernel = (kernel >= 1 && kernel <= 3) ? kernel : 3;
+    return prev;
+}
 
 int sa_set_seed_shape(const char *pattern) {
     if (!pattern) return fail(SA_ERR_ARG, "pattern is NULL");
