@@ -26,7 +26,8 @@ constexpr int SCR_STAGE_STRIDE = 7;  // uint4 slots per hit in the staging buffe
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
 constexpr int SCR_RING = 256;        // staged hits per warp (ring, power of two)
 constexpr int SCR_ROWS = 64;         // aligned query rows per warp (ring, power of two)
-constexpr int SCR_REFILL = 64;       // refill the ring when fewer hits than this are staged (two rounds)
+constexpr int SCR_REFILL = 96;       // refill the ring when fewer hits than this are staged (three rounds:
+                                     // the positions of round n+1 were copied in before the refill of round n)
 constexpr int SCR_Q_CAP = 96;
 constexpr int SCR_Q_DRAIN = 64;
 constexpr int SCR_WARPS = FILTER_THREADS / 32;
@@ -41,13 +42,21 @@ constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STA
 constexpr size_t SCR_OFF_RING = SCR_OFF_ROWS + (size_t)SCR_WARPS * SCR_ROWS * SCR_ROW_STRIDE * 4;
 constexpr size_t SCR_OFF_QUEUE = SCR_OFF_RING + (size_t)SCR_WARPS * SCR_RING * 4;
 constexpr size_t SCR_OFF_RROW = SCR_OFF_QUEUE + (size_t)SCR_WARPS * SCR_Q_CAP * 8;
-constexpr size_t SCR_SMEM_BYTES = SCR_OFF_RROW + (size_t)SCR_WARPS * SCR_RING;
+constexpr size_t SCR_OFF_DELTA = SCR_OFF_RROW + (size_t)SCR_WARPS * SCR_RING;
+constexpr size_t SCR_SMEM_BYTES = SCR_OFF_DELTA + (size_t)SCR_WARPS * SCR_ROWS * 4;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
     ScreenRec r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
@@ -56,10 +65,12 @@ __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
 
 // Work flow of one warp (all state below is warp-uniform unless it says "lane"):
 //   refill   while fewer than SCR_REFILL hits are staged: take the next group of 32 seed words
-//            (global counter), look their buckets up, align the query window of every seed word
-//            that has hits into a row of the row ring, expand the buckets into the hit ring
-//            (reference position + row id per hit).  Hits of different groups queue up behind
-//            each other, so every round below has 32 hits until the very end of the call.
+//            (global counter, fetched one refill ahead), look their buckets up, align the query
+//            window of every seed word that has hits into a row of the row ring, expand the
+//            buckets into the hit ring (reference position + row id per hit; the positions are
+//            copied from the seed position table with cp.async and are first read two rounds
+//            later).  Hits of different groups queue up behind each other, so every round below
+//            has 32 hits until the very end of the call.
 //   round    the 32 oldest staged hits, one per lane: their reference records were requested by
 //            the previous round (cp.async into the staging buffer); the owner lanes pull them
 //            into registers, the requests of the NEXT round go out, then the screen runs -- the
@@ -93,11 +104,14 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t *ring_r = reinterpret_cast<uint32_t *>(smem + SCR_OFF_RING) + warp * SCR_RING;
     uint32_t *myq = reinterpret_cast<uint32_t *>(smem + SCR_OFF_QUEUE) + warp * SCR_Q_CAP * 2;
     uint8_t *ring_row = reinterpret_cast<uint8_t *>(smem + SCR_OFF_RROW) + warp * SCR_RING;
+    uint32_t *rowdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS; // bucket start - exclusive hit prefix, per row
     const uint4 *rrec_m3 = P.rrec - 3; // record w-3 of a window (REC_FRONT >= 3 records of front padding)
 
     const uint32_t total_items = H.num_items;
     uint32_t key_base = 0, g_total = 0, g_done = 0, g_row_base = 0;
     uint32_t head = 0, tail = 0;   // hit ring: [head, tail) staged and not yet screened (monotonic counters)
+    uint32_t next_c = 0;           // lane 0: the next group number, fetched one refill ahead
+    if (lane == 0) next_c = atomicAdd(counters + CTR_CHUNK, 1u);
     uint32_t row_tail = 0;         // rows handed out so far (monotonic; row id = counter mod 256)
     uint32_t pre_n = 0;            // hits whose records are already requested (the next round)
     bool exhausted = false;
@@ -106,9 +120,10 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t qcount = 0; // queued undecided hits
     uint32_t ext_tiles = 0, acc_walked = 0;
 
-    auto emit = [&](uint32_t r0, uint32_t q0, uint32_t key) {
-        const uint32_t slot = atomicAdd(counters + CTR_SURV, 1u);
-        if (slot < surv_cap) { SurvRec rec; rec.r0 = r0; rec.q0 = q0; rec.key = key; surv[slot] = rec; }
+    // query anchor of a hit from the order index of its seed word
+    auto query_anchor = [&](uint32_t key) -> uint32_t {
+        const uint32_t qpos = SRC == SRC_RANGE ? H.j0 + key / H.per : (uint32_t)__ldg(H.seeds + key);
+        return qpos + H.seed_size;
     };
     // reference records w-3 .. w+2 of n staged hits starting at ring position `from`: six
     // neighbouring lanes per hit, 16 bytes each, straight into the staging buffer
@@ -118,7 +133,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             const uint32_t f = i * 32u + lane;
             const uint32_t hs = f / SCREEN_RECS, rc = f - hs * SCREEN_RECS;
             if (hs < n) {
-                const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)];
+                const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)] + H.seed_size;
                 cp_async16(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc));
             }
         }
@@ -126,6 +141,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
 
     for (;;) {
         // ---------------- refill the hit ring
+        const uint32_t tail_prev = tail; // positions below this were copied in by an earlier refill
         while (tail - head < (uint32_t)SCR_REFILL && !exhausted) {
             const bool new_group = g_done == g_total;
             if (new_group) {
@@ -134,11 +150,10 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     const uint32_t live = (row_tail - ring_row[head & (SCR_RING - 1)]) & 0xFFu;
                     if (live > (uint32_t)(SCR_ROWS - 32)) break; // then more than 32 hits are staged: screen first
                 }
-                uint32_t c = 0;
-                if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
-                c = __shfl_sync(0xFFFFFFFFu, c, 0);
+                const uint32_t c = __shfl_sync(0xFFFFFFFFu, next_c, 0);
                 const unsigned long long start = (unsigned long long)c * 32u;
                 if (start >= total_items) { exhausted = true; break; }
+                if (lane == 0) next_c = atomicAdd(counters + CTR_CHUNK, 1u);
                 key_base = (uint32_t)start;
                 g_done = 0;
             }
@@ -196,51 +211,61 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     dst[0] = make_uint4(row[0], row[1], row[2], row[3]);
                     dst[1] = make_uint4(row[4], row[5], row[6], row[7]);
                     dst[2] = make_uint4(row[8], row[9], row[10], k); // word 11 = seed order index of the row
+                    rowdelta[slot] = b_start - excl; // hit f of the group sits at pos_table[f + this]
                 }
                 row_tail += __popc(with_hits);
             }
             const uint32_t cnt = min(g_total - g_done, (uint32_t)SCR_RING - (tail - head));
             __syncwarp();
             for (uint32_t kk = 0; kk * 32u < cnt; kk++) {
-                const uint32_t f = g_done + kk * 32u + lane; // flat index inside the group
-                uint32_t lo = 0, hi = 31;                    // owner = first lane whose inclusive prefix exceeds f
-#pragma unroll
-                for (int it = 0; it < 5; it++) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    const uint32_t vmid = __shfl_sync(0xFFFFFFFFu, incl, mid);
-                    if (vmid > f) hi = mid; else lo = mid + 1;
-                }
-                const uint32_t o_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
-                const uint32_t o_start = __shfl_sync(0xFFFFFFFFu, b_start, lo);
+                // owner of hit f = the j-th seed word with hits, j = #{words with hits whose inclusive
+                // prefix is <= f}: one ballot for the 32 hits' common base, one OR-reduction of the
+                // prefix boundaries that fall inside these 32 hits, one popcount per lane
+                const uint32_t f0 = g_done + kk * 32u;
+                const uint32_t j0 = __popc(__ballot_sync(0xFFFFFFFFu, n > 0 && incl <= f0));
+                const uint32_t bp = incl - f0 - 1u;
+                const uint32_t bounds = __reduce_or_sync(0xFFFFFFFFu, (n > 0 && incl > f0 && bp < 32u) ? 1u << bp : 0u);
+                const uint32_t rowid = g_row_base + j0 + __popc(bounds & lt_mask);
                 if (kk * 32u + lane < cnt) {
                     const uint32_t slot = (tail + kk * 32u + lane) & (uint32_t)(SCR_RING - 1);
-                    ring_r[slot] = __ldg(H.pos_table + o_start + (f - o_excl)) + H.seed_size;
-                    ring_row[slot] = (uint8_t)(g_row_base + __popc(with_hits & ((1u << lo) - 1u)));
+                    cp_async4(ring_r + slot, H.pos_table + (rowdelta[rowid & (uint32_t)(SCR_ROWS - 1)] + f0 + lane));
+                    ring_row[slot] = (uint8_t)rowid;
                 }
             }
             __syncwarp();
             g_done += cnt;
             tail += cnt;
         }
+        cp_async_commit(); // group "A": the positions staged by this refill (possibly none)
         if (tail == head && qcount == 0) break; // exhausted, everything screened and walked
 
         // ---------------- one round of the screen: the 32 oldest staged hits, one per lane
         if (tail != head) {
-            const uint32_t n1 = pre_n ? pre_n : min(tail - head, 32u);
-            if (!pre_n) request_records(head, n1);
+            // cp.async groups in issue order: ... R(this round) A(this refill) | R(next round) ...
+            uint32_t n1 = pre_n, safe_tail = tail_prev;
+            if (!pre_n) { // cold: nothing requested yet (start of the call, or the ring ran dry)
+                cp_async_wait_all();
+                __syncwarp();
+                n1 = min(tail - head, 32u);
+                safe_tail = tail;
+                request_records(head, n1);
+                cp_async_commit();
+                cp_async_wait_all();
+            } else {
+                cp_async_wait_group<1>(); // everything but this refill's positions has landed
+            }
             const bool have = lane < n1;
             uint32_t r0 = 0, rowid = 0;
             if (have) {
                 const uint32_t slot = (head + lane) & (uint32_t)(SCR_RING - 1);
-                r0 = ring_r[slot];
                 rowid = ring_row[slot];
             }
             const uint4 *qrow = reinterpret_cast<const uint4 *>(rows + (rowid & (uint32_t)(SCR_ROWS - 1)) * SCR_ROW_STRIDE);
             const uint4 q_a = qrow[0], q_b = qrow[1], q_c = qrow[2];
             const uint32_t qr[SCREEN_ROW_WORDS] = {q_a.x, q_a.y, q_a.z, q_a.w, q_b.x, q_b.y, q_b.z, q_b.w, q_c.x, q_c.y, q_c.z, 0u};
             const uint32_t key = q_c.w;
-            cp_async_wait_all();
             __syncwarp();
+            if (have) r0 = ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size;
             uint32_t rr[SCREEN_ROW_WORDS];
             {
                 const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
@@ -250,8 +275,9 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             }
             __syncwarp(); // every lane holds its window: the staging buffer is free again
             head += n1;
-            pre_n = min(tail - head, 32u);
+            pre_n = min(safe_tail - head, 32u); // only positions that are known to have landed
             if (pre_n) request_records(head, pre_n);
+            cp_async_commit(); // group "R": the records of the next round
             int bound; bool decided;
             const bool push = have && !screen_reject(rr, qr, C, bound, decided);
             const unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
@@ -266,7 +292,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
 
         // ---------------- tile walk of the undecided hits (persistent lanes, kernels_filter.cuh)
         if (qcount >= (uint32_t)SCR_Q_DRAIN || (qcount > 0 && tail == head && exhausted)) {
-            uint32_t qhead = 0;
+            uint32_t qhead = 0, nsurv = 0;
             bool active = false, left = false;
             uint32_t key = 0, r0 = 0, q0 = 0, t = 0;
             int s = 0, M = 0, right_score = 0;
@@ -278,8 +304,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     if (!active && rank < avail) {
                         const uint32_t idx = qhead + rank;
                         r0 = myq[idx * 2 + 0]; key = myq[idx * 2 + 1];
-                        const uint32_t qpos = SRC == SRC_RANGE ? H.j0 + key / H.per : (uint32_t)__ldg(H.seeds + key);
-                        q0 = qpos + H.seed_size;
+                        q0 = query_anchor(key);
                         t = 0; s = 0; M = 0; right_score = 0; left = false;
                         active = true;
                     }
@@ -287,6 +312,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     qhead += nneed < avail ? nneed : avail;
                 }
                 if (!__any_sync(0xFFFFFFFFu, active)) break;
+                bool keep = false;
                 if (active) {
                     const int cr = left ? (int)r0 - (int)t - 32 : (int)r0 + (int)t;
                     const int cq = left ? (int)q0 - (int)t - 32 : (int)q0 + (int)t;
@@ -298,7 +324,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     tile_walk(lut_lane, mul, m4, diag, P, R, Q, Tr | Tq, Sr | Sq, left, s, M, done, survive);
                     ext_tiles += t >= 32u ? 1u : 0u;
                     if (survive || (left ? right_score : 0) + M >= thr) {
-                        emit(r0, q0, key);
+                        keep = true;
                         active = false;
                     } else if (done) {
                         if (!left) { right_score = M; left = true; t = 0; s = 0; M = 0; }
@@ -306,6 +332,25 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     } else {
                         t += 32u;
                     }
+                }
+                // survivors go back into the part of the queue that has already been handed out
+                // (one global atomic per drain instead of one per survivor)
+                const unsigned km = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) {
+                    const uint32_t idx = nsurv + __popc(km & lt_mask);
+                    myq[idx * 2 + 0] = r0; myq[idx * 2 + 1] = key;
+                }
+                nsurv += __popc(km);
+            }
+            __syncwarp();
+            if (nsurv) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(counters + CTR_SURV, nsurv);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                for (uint32_t i = lane; i < nsurv; i += 32u) {
+                    SurvRec rec;
+                    rec.r0 = myq[i * 2 + 0]; rec.key = myq[i * 2 + 1]; rec.q0 = query_anchor(rec.key);
+                    if (base + i < surv_cap) surv[base + i] = rec;
                 }
             }
             qcount = 0;
