@@ -9,6 +9,10 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/${TAG}_g
 timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
 echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
 tail -3 $OUT/${TAG}_pytest.log
+if [ -n "$CHECK_LARGE" ]; then
+  timeout 900 python tests/golden/check_large.py $CHECK_LARGE > $OUT/${TAG}_check_large.json 2> $OUT/${TAG}_check_large.err
+  echo "check_large exit $?"; cat $OUT/${TAG}_check_large.json | cut -c1-700
+fi
 for K in $KERNELS; do
   SEGALIGN_B200_FILTER_KERNEL=$K timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline \
       > $OUT/${TAG}_bench_k$K.json 2> $OUT/${TAG}_bench_k$K.err

@@ -283,8 +283,9 @@ __device__ __forceinline__ bool dedup_is_new(const DedupTable &T, const sa_segme
 constexpr int EXTEND_THREADS = 32; // one warp per block: fits beside the resident filter blocks
 
 // counters: see the CTR_* enum (kernels_filter.cuh).
-// With surv != nullptr the kernel walks the survivor records of the filter kernel (their count is
-// read from counters[CTR_SURV] on the device so the host need not synchronise in between);
+// With surv != nullptr the kernel walks survivor records (those of the filter kernel, or the ones
+// k_extend_wide handed on; their count is read from counters[surv_ctr] on the device so the host
+// need not synchronise in between);
 // otherwise it walks hits [0, min(plan[1], h_end)) directly.  Lanes 2i / 2i+1 of a warp extend work
 // item i to the right / to the left.
 // Iteration tag of a hit (dedupe scope): general path = position of the hit index in
@@ -292,7 +293,7 @@ constexpr int EXTEND_THREADS = 32; // one warp per block: fits beside the reside
 // words before the last hit-bearing seed word, 1 from that seed word on.
 __global__ void __launch_bounds__(EXTEND_THREADS)
 k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              uint32_t h_end, const SurvRec *__restrict__ surv, uint32_t surv_cap, int fused,
+              uint32_t h_end, const SurvRec *__restrict__ surv, uint32_t surv_cap, int surv_ctr, int fused,
               const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors,
               uint32_t anchor_cap, uint32_t *__restrict__ counters, DedupTable dedup) {
@@ -303,7 +304,7 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
     if (threadIdx.x < 16) lut16[threadIdx.x] = sub_mat[(threadIdx.x >> 2) * 8 + (threadIdx.x & 3)];
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
-    h_end = surv ? min(counters[CTR_SURV], surv_cap) : min(plan[1], h_end); // counts known only on the device
+    h_end = surv ? min(counters[surv_ctr], surv_cap) : min(plan[1], h_end); // counts known only on the device
     const uint32_t items_per_pass = (gridDim.x * blockDim.x) >> 1;
     const bool left = threadIdx.x & 1u;
     unsigned long long cells = 0;

@@ -22,6 +22,7 @@
 
 #include "kernels_encode.cuh"
 #include "kernels_extend.cuh"
+#include "kernels_extend_wide.cuh"
 #include "kernels_filter.cuh"
 #include "kernels_lookup.cuh"
 #include "kernels_screen.cuh"
@@ -96,6 +97,7 @@ struct Workspace {
     uint32_t *d_counters = nullptr;  // CTR_WORDS counters, see the CTR_* enum (kernels_filter.cuh)
     uint2 *d_hits = nullptr; size_t hits_cap = 0;
     SurvRec *d_surv = nullptr; size_t surv_cap = 0;  // filter survivors (anchor pair + key)
+    SurvRec *d_surv2 = nullptr; size_t surv2_cap = 0; // survivors k_extend_wide hands on to k_extend_hits
     unsigned long long *d_dedup = nullptr;           // exact-duplicate table: k0[slots], k1[slots], tagbits[slots]
     Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
     Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
@@ -137,6 +139,8 @@ struct Global {
     int filter_kernel = 3;     // SEGALIGN_B200_FILTER_KERNEL=1|2 select the single-phase / two-phase tile-walk kernels
     ScreenConsts screen = {};  // class scores of the popcount screen (screen_bound.h)
     int extend_grid = 0;
+    int wide_grid = 0;         // k_extend_wide (warp per hit), SEGALIGN_B200_WIDE=0 sends all survivors to k_extend_hits
+    bool use_wide = true;
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
     uint32_t query_len[SA_BUFFER_DEPTH] = {};
@@ -269,7 +273,7 @@ int make_workspace(int gpu_index, Workspace *&out) {
 void destroy_workspace(Workspace *w) {
     cudaFree(w->d_seeds); cudaFree(w->d_prefix); cudaFree(w->d_limit_pos);
     cudaFree(w->d_hit_bound); cudaFree(w->d_plan); cudaFree(w->d_counters);
-    cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_dedup); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
+    cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_surv2); cudaFree(w->d_dedup); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
     cudaFreeHost(w->h_out);
@@ -454,9 +458,20 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             }
         }
         // 4b. stage B: exact extension of the survivors (seed_filter.cu:762-774)
-        k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
-            P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, surv_cap, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
-            w->d_anchors_a, anchor_cap, w->d_counters, D);
+        if (filter && G.use_wide) {
+            // warp-per-hit pass over all survivors; what needs the entropy counters goes on to the lane-pair kernel
+            if (w->surv2_cap < w->surv_cap) TRY(ensure(w->d_surv2, w->surv2_cap, w->surv_cap, "survivors2", 1, 1));
+            k_extend_wide<<<G.wide_grid, WIDE_THREADS, 0, st>>>(P, g.d_sub_mat, w->d_surv, surv_cap, w->d_surv2, fused ? 1 : 0,
+                                                                w->d_hit_bound, w->d_plan, w->d_anchors_a, anchor_cap, w->d_counters, D);
+            k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
+                P, g.d_sub_mat, w->d_hits, hits_cap, w->d_surv2, surv_cap, (int)CTR_SURV2, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
+                w->d_anchors_a, anchor_cap, w->d_counters, D);
+            launches++;
+        } else {
+            k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
+                P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, surv_cap, (int)CTR_SURV, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
+                w->d_anchors_a, anchor_cap, w->d_counters, D);
+        }
         pt.mark(PH_EXTEND);
         // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the anchors
         //    fit; the counters, the plan and the first FINALIZE_CAP records come back together
@@ -678,6 +693,10 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         G.filter_kernel = 3;
         if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) { int v = atoi(e); if (v >= 1 && v <= 3) G.filter_kernel = v; }
         G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
+        if (const char *e = getenv("SEGALIGN_B200_EXTEND_CTAS")) if (atoi(e) > 0) G.extend_grid = atoi(e) * std::max(1, sms);
+        G.wide_grid = 4 * std::max(1, sms);   // four-warp blocks, one warp per hit
+        if (const char *e = getenv("SEGALIGN_B200_WIDE_CTAS")) if (atoi(e) > 0) G.wide_grid = atoi(e) * std::max(1, sms);
+        { const char *e = getenv("SEGALIGN_B200_WIDE"); G.use_wide = !(e && atoi(e) == 0); }
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
         for (SeqPlanes *p : all)

@@ -63,6 +63,17 @@ def test_tile_walk_kernels_match_reference_golden(backend, case, kernel, device_
     H.assert_calls_equal(got, want, f"filter kernel {kernel} vs reference golden")
 
 
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+def test_lane_pair_exact_kernel_alone_matches_reference_golden(backend, case, monkeypatch):
+    """SEGALIGN_B200_WIDE=0: every survivor goes to k_extend_hits (two lanes per hit) instead of
+    the warp-per-hit kernel k_extend_wide, which otherwise handles all hits that need no entropy
+    factor.  Both must give the reference's bytes."""
+    monkeypatch.setenv("SEGALIGN_B200_WIDE", "0")
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=True)
+    H.assert_calls_equal(got, want, "lane-pair exact kernel alone vs reference golden")
+
+
 def test_screen_decides_most_random_hits(backend):
     """The popcount screen (default kernel) must be live -- few hits reach the tile walk on a
     diverged random pair -- and the tile-walk-only kernel must report none."""
