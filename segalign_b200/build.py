@@ -44,7 +44,8 @@ def build_backend(force: bool = False, verbose: bool = False) -> Path:
     sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.inc")) + [ROOT / "include" / "segalign_b200.h"]
     if not force and _newer(LIB, sources):
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), str(CSRC / "sa_backend.cu")]
+    extra = os.environ.get("SEGALIGN_B200_NVCC_EXTRA", "").split()  # e.g. -DSA_SCR_THREADS=288 (tuning experiments)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", str(LIB), str(CSRC / "sa_backend.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=str(CSRC))

@@ -22,15 +22,29 @@
 
 namespace sa {
 
-constexpr int SCR_STAGE_STRIDE = 7;  // uint4 slots per hit in the staging buffer (6 used; 7 = conflict-free LDS.128)
+// tuning knobs (overridable at build time: scripts/tune_filter3.sh measures the variants on the GPU)
+#ifndef SA_SCR_THREADS
+#define SA_SCR_THREADS 256
+#endif
+#ifndef SA_SCR_MIN_CTAS
+#define SA_SCR_MIN_CTAS 3
+#endif
+#ifndef SA_SCR_STAGE_STRIDE
+#define SA_SCR_STAGE_STRIDE 7
+#endif
+#ifndef SA_SCR_Q_CAP
+#define SA_SCR_Q_CAP 96
+#endif
+constexpr int SCR_THREADS = SA_SCR_THREADS;
+constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint4 slots per hit in the staging buffer (6 used; 7 = conflict-free LDS.128)
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
 constexpr int SCR_RING = 256;        // staged hits per warp (ring, power of two)
 constexpr int SCR_ROWS = 64;         // aligned query rows per warp (ring, power of two)
 constexpr int SCR_REFILL = 96;       // refill the ring when fewer hits than this are staged (three rounds:
                                      // the positions of round n+1 were copied in before the refill of round n)
-constexpr int SCR_Q_CAP = 96;
-constexpr int SCR_Q_DRAIN = 64;
-constexpr int SCR_WARPS = FILTER_THREADS / 32;
+constexpr int SCR_Q_CAP = SA_SCR_Q_CAP;
+constexpr int SCR_Q_DRAIN = SCR_Q_CAP - 32;
+constexpr int SCR_WARPS = SCR_THREADS / 32;
 constexpr int SCR_LUT_COLS = 4;      // pair-LUT replicas (the tile walk is ~6 % of this kernel: conflicts are cheap)
 constexpr int SCR_LUT_WORDS = 256 * SCR_LUT_COLS;
 constexpr uint32_t SCR_K_MUL = 1u | (16u << 8); // dp2a multipliers of group_scores for a 4-column LUT
@@ -44,6 +58,8 @@ constexpr size_t SCR_OFF_QUEUE = SCR_OFF_RING + (size_t)SCR_WARPS * SCR_RING * 4
 constexpr size_t SCR_OFF_RROW = SCR_OFF_QUEUE + (size_t)SCR_WARPS * SCR_Q_CAP * 8;
 constexpr size_t SCR_OFF_DELTA = SCR_OFF_RROW + (size_t)SCR_WARPS * SCR_RING;
 constexpr size_t SCR_SMEM_BYTES = SCR_OFF_DELTA + (size_t)SCR_WARPS * SCR_ROWS * 4;
+static_assert((SCR_SMEM_BYTES + 1024) * SA_SCR_MIN_CTAS <= 233472, "k_filter_hits3: shared memory of the resident blocks exceeds an SM");
+static_assert(SCR_Q_DRAIN >= 1 && SCR_Q_CAP >= SCR_Q_DRAIN + 31, "a round may queue 32 hits after the drain threshold was missed");
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -78,7 +94,7 @@ __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
 //   drain    undecided hits (reference anchor + seed index) wait in a per-warp queue and are
 //            tile-walked SCR_Q_DRAIN at a time.
 template <int SRC>
-__global__ void __launch_bounds__(FILTER_THREADS, 3)
+__global__ void __launch_bounds__(SCR_THREADS, SA_SCR_MIN_CTAS)
 k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restrict__ sub_mat,
                SurvRec *__restrict__ surv, uint32_t surv_cap, uint32_t *__restrict__ counters) {
     static_assert(SRC == SRC_SEEDS || SRC == SRC_RANGE, "the screen needs the seed word of every hit");

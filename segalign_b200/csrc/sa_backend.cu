@@ -406,9 +406,9 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
                 FilterParams F3 = F;
                 F3.k_mul = SCR_K_MUL;
                 if (in.src == SRC_SEEDS)
-                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 else
-                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, FILTER_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
             } else if (G.filter_kernel == 1) {
                 if (in.src == SRC_SEEDS)
                     k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
@@ -687,7 +687,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaFuncSetAttribute(k_filter_hits3<SRC_RANGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCR_SMEM_BYTES), SA_ERR_KERNEL);
         CU(cudaFuncSetAttribute(k_filter_hits3<SRC_SEEDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCR_SMEM_BYTES), SA_ERR_KERNEL);
         int per_sm3 = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_filter_hits3<SRC_RANGE>, FILTER_THREADS, SCR_SMEM_BYTES), SA_ERR_KERNEL);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_filter_hits3<SRC_RANGE>, SCR_THREADS, SCR_SMEM_BYTES), SA_ERR_KERNEL);
         if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm3 = std::min(per_sm3, atoi(e));
         G.filter3_grid = std::max(1, per_sm3) * std::max(1, sms);
         G.filter_kernel = 3;
