@@ -21,9 +21,10 @@ Numbers on the JSON line:
             query block is uploaded (sa_send_query), every unit's seed vector is built on the
             host (sa_host_chunk_seeds == src/seeder.cpp:57-74) and handed to
             sa_seed_and_filter (== g_SeedAndFilter), HSPs come back to host memory.
-  roofline  k_filter_hits (the dominant kernel: the extension's score filter over ALL hits):
-            algorithmic bytes 64*H + E (SURVEY 8d B_X) per launch / CUDA-event duration of that
-            kernel on its own stream inside the timed region, vs MEASURED_PEAKS hbm.
+  roofline  k_filter_hits3 (the dominant kernel: seeding + lookup + bucket expansion + the score
+            filter over ALL hits): algorithmic bytes 16*S + 4*H + 64*H + E (SURVEY 8d B_L + B_X)
+            per launch / CUDA-event duration of that kernel on its own stream in a serialized pass
+            right after the timed region, vs MEASURED_PEAKS hbm.
   cpu_baseline  LASTZ (oracle/_ref/lastz, built from the reference's submodule) on a bounded
             sample of the same workload, one process per host core.
 """
@@ -316,7 +317,7 @@ def run_ours(args):
     t_ext = st_probe["ms_prefilter"] * 1e-3
     achieved = alg_bytes / t_ext / 1e9 if t_ext > 0 else 0.0
     step_bytes = 16.0 * st_res["seeds"] + 68.0 * st_res["hits"] + ext_per_hit * st_res["hits"]
-    roofline = {"bound": "hbm", "kernel": "k_filter_hits", "achieved": round(achieved, 1), "peak": peak,
+    roofline = {"bound": "hbm", "kernel": "k_filter_hits%s" % ("3" if prev_kernel == 3 else ("2" if prev_kernel == 2 else "")), "achieved": round(achieved, 1), "peak": peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650",
                 "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
@@ -326,7 +327,7 @@ def run_ours(args):
                 "bytes_formula": "16*S + 4*H (seed lookup, fused into this kernel) + 64*H + E (extension), per rank; "
                                  "E counted by an untimed pass of the tile-walk-only kernel over the same units",
                 "filter_kernel": int(prev_kernel),
-                "lookup": {"fused_into": "k_filter_hits", "algorithmic_bytes_per_launch": round(lookup_bytes / n_launch)},
+                "lookup": {"fused_into": "the same kernel", "algorithmic_bytes_per_launch": round(lookup_bytes / n_launch)},
                 "whole_step": {"algorithmic_GBps": round(step_bytes / (ms_res * 1e-3) / 1e9, 1),
                                "frac": round(step_bytes / (ms_res * 1e-3) / 1e9 / peak, 4),
                                "note": "all kernels + host gaps of the timed region, rank 0"},
