@@ -139,6 +139,39 @@ typedef struct sa_chrom_table {
 int sa_write_segments(const char *path, const sa_segment *hsps, uint32_t n, int minus, uint64_t r_block_start,
                       uint64_t q_block_start, const sa_chrom_table *ref_chroms, const sa_chrom_table *query_chroms);
 
+/* Whole-genome driver -- what src/main.cpp does around the hot path, without Boost
+ * or TBB: FASTA records -> '&'-separated blocks (src/main.cpp:336-415, :479-541), seeding
+ * intervals (:380-393), the block schedule of the reader node (:600-741: every reference block
+ * against every query block, query blocks double-buffered in the two device slots), and the
+ * output of segment_printer_body (src/segment_printer.cpp:38-170) into out_dir:
+ *   tmp<interval>.block<q>.r<ref block offset>.{plus,minus}.segments, ref_block<i>.name,
+ *   query_block<i>.name, lastz_commands.txt (one LASTZ command per segments file; also printed to
+ *   stdout when gapped != 0, as the reference does).
+ * Zero / NULL fields take the reference's defaults (src/main.cpp:60-120, src/graph.h:10-12).
+ * Calls sa_initialize_interface ... sa_shutdown_processor itself.  Plain-text FASTA only. */
+typedef struct sa_pipeline_config {
+    const char *ref_fasta, *query_fasta, *out_dir;
+    const char *data_folder;   /* prefix of ref.2bit / query.2bit in the LASTZ command lines */
+    const char *seed_shape;    /* "12of19" (default), "14of22" or a 0/1 pattern */
+    const char *strand;        /* "plus", "minus", "both" (default) */
+    const char *ambiguous;     /* "", "n", "iupac" or "x,R,P" */
+    const char *output_format; /* default "maf-" */
+    const char *scoring_file;  /* only forwarded to the command lines */
+    const int *sub_mat;        /* 8x8 matrix; NULL = built by sa_build_matrix(ambiguous, xdrop) */
+    int transition, noentropy, gapped, notrivial;
+    int xdrop, ydrop, hspthresh, gappedthresh;
+    uint32_t step, wga_chunk, lastz_interval;
+    uint64_t seq_block_size;
+    int num_gpu, num_threads;
+} sa_pipeline_config;
+typedef struct sa_pipeline_report {
+    uint64_t ref_blocks, query_blocks, intervals, calls, seeds, hits, hsps, segment_files;
+    double seconds;
+} sa_pipeline_report;
+int sa_pipeline_run(const sa_pipeline_config *cfg, sa_pipeline_report *report);
+/* src/main.cpp:187-268: the substitution matrix of --ambiguous / --xdrop (no --scoring file) */
+int sa_build_matrix(const char *ambiguous, int xdrop, int *sub_mat);
+
 /* ShutdownProcessor -- src/seed_filter.cu:932-940 */
 int sa_shutdown_processor(void);
 

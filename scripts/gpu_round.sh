@@ -18,6 +18,16 @@ for K in $KERNELS; do
       > $OUT/${TAG}_bench_k$K.json 2> $OUT/${TAG}_bench_k$K.err
   echo "bench k=$K exit $?"; cat $OUT/${TAG}_bench_k$K.json | cut -c1-600
 done
+if [ -n "$EXTRA_BUILDS" ]; then   # "name:flags;name:flags": rebuild on the box and bench each variant
+  IFS=';' read -ra VARS <<< "$EXTRA_BUILDS"
+  for V in "${VARS[@]}"; do
+    NAME=${V%%:*}; FLAGS=${V#*:}
+    SEGALIGN_B200_NVCC_EXTRA="$FLAGS" python -c "from segalign_b200.build import build_backend; build_backend(force=True)"
+    timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_$NAME.json 2> $OUT/${TAG}_bench_$NAME.err
+    echo "variant $NAME ($FLAGS): $(python -c "import json;d=json.load(open('$OUT/${TAG}_bench_$NAME.json'));print(d['value'],d['ms_per_step'],d['roofline']['avg_launch_ms'],d['e2e']['value'])")"
+  done
+  python -c "from segalign_b200.build import build_backend; build_backend(force=True)"
+fi
 K=${KERNELS%% *}
 export SEGALIGN_B200_FILTER_KERNEL=$K
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv \

@@ -23,6 +23,7 @@ ABI_SYMBOLS = [
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
     "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds", "sa_write_segments",
+    "sa_pipeline_run", "sa_build_matrix",
 ]
 
 
@@ -33,6 +34,25 @@ class SaStats(C.Structure):
                 ("ms_h2d", "ms_count_scan", "ms_lookup", "ms_prefilter", "ms_extend", "ms_sort",
                  "ms_d2h", "ms_ref_encode", "ms_table_build", "ms_query_encode")] + \
                [("launches", C.c_uint64), ("walked", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SaPipelineConfig(C.Structure):
+    _fields_ = [(n, C.c_char_p) for n in
+                ("ref_fasta", "query_fasta", "out_dir", "data_folder", "seed_shape", "strand", "ambiguous",
+                 "output_format", "scoring_file")] + \
+               [("sub_mat", C.POINTER(C.c_int))] + \
+               [(n, C.c_int) for n in ("transition", "noentropy", "gapped", "notrivial", "xdrop", "ydrop",
+                                       "hspthresh", "gappedthresh")] + \
+               [(n, C.c_uint32) for n in ("step", "wga_chunk", "lastz_interval")] + \
+               [("seq_block_size", C.c_uint64), ("num_gpu", C.c_int), ("num_threads", C.c_int)]
+
+
+class SaPipelineReport(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("ref_blocks", "query_blocks", "intervals", "calls", "seeds", "hits",
+                                          "hsps", "segment_files")] + [("seconds", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -75,6 +95,8 @@ def load_library(path: Path | None = None) -> C.CDLL:
                                             C.c_int, C.c_int, C.c_int]
     lib.sa_set_max_hits.argtypes = [C.c_uint32]
     lib.sa_set_filter_kernel.argtypes = [C.c_int]
+    lib.sa_build_matrix.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+    lib.sa_pipeline_run.argtypes = [C.c_void_p, C.c_void_p]
     lib.sa_set_seed_shape.argtypes = [C.c_char_p]
     lib.sa_send_ref.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     lib.sa_generate_seed_pos_table.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
@@ -210,6 +232,29 @@ class Backend:
 
     def get_max_hits(self) -> int:
         return self.lib.sa_get_max_hits()
+
+    def build_matrix(self, ambiguous: str, xdrop: int) -> np.ndarray:
+        m = np.zeros(64, dtype=np.int32)
+        self._check(self.lib.sa_build_matrix(ambiguous.encode(), int(xdrop), m.ctypes.data_as(C.POINTER(C.c_int))))
+        return m
+
+    def pipeline_run(self, ref_fasta, query_fasta, out_dir, **kw) -> dict:
+        """sa_pipeline_run: the Boost-free whole-genome driver."""
+        cfg = SaPipelineConfig()
+        cfg.ref_fasta, cfg.query_fasta, cfg.out_dir = str(ref_fasta).encode(), str(query_fasta).encode(), str(out_dir).encode()
+        keep = []
+        for k, v in kw.items():
+            if k == "sub_mat":
+                arr = np.ascontiguousarray(v, dtype=np.int32)
+                keep.append(arr)
+                cfg.sub_mat = arr.ctypes.data_as(C.POINTER(C.c_int))
+            elif isinstance(v, str):
+                setattr(cfg, k, v.encode())
+            else:
+                setattr(cfg, k, int(v))
+        rep = SaPipelineReport()
+        self._check(self.lib.sa_pipeline_run(C.byref(cfg), C.byref(rep)))
+        return rep.as_dict()
 
     def set_filter_kernel(self, k: int) -> int:
         return self.lib.sa_set_filter_kernel(int(k))

@@ -35,6 +35,9 @@ namespace sa {
 #ifndef SA_SCR_Q_CAP
 #define SA_SCR_Q_CAP 96
 #endif
+#ifndef SA_SCR_L2_HINTS
+#define SA_SCR_L2_HINTS 1 // reference records evict_last, seed positions evict_first (keeps the records L2-resident)
+#endif
 constexpr int SCR_THREADS = SA_SCR_THREADS;
 constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint4 slots per hit in the staging buffer (6 used; 7 = conflict-free LDS.128)
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
@@ -68,6 +71,26 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+// L2 cache policies: the reference records are gathered again and again by every call of a block
+// (50 MB at 100 Mb: they fit the L2), the seed positions stream through once per call
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(void *smem_dst, const void *gmem_src, uint64_t policy) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async4_hint(void *smem_dst, const void *gmem_src, uint64_t policy) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
@@ -122,6 +145,9 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint8_t *ring_row = reinterpret_cast<uint8_t *>(smem + SCR_OFF_RROW) + warp * SCR_RING;
     uint32_t *rowdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS; // bucket start - exclusive hit prefix, per row
     const uint4 *rrec_m3 = P.rrec - 3; // record w-3 of a window (REC_FRONT >= 3 records of front padding)
+#if SA_SCR_L2_HINTS
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+#endif
 
     const uint32_t total_items = H.num_items;
     uint32_t key_base = 0, g_total = 0, g_done = 0, g_row_base = 0;
@@ -150,7 +176,11 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             const uint32_t hs = f / SCREEN_RECS, rc = f - hs * SCREEN_RECS;
             if (hs < n) {
                 const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)] + H.seed_size;
+#if SA_SCR_L2_HINTS
+                cp_async16_hint(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc), pol_keep);
+#else
                 cp_async16(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc));
+#endif
             }
         }
     };
@@ -244,7 +274,11 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 const uint32_t rowid = g_row_base + j0 + __popc(bounds & lt_mask);
                 if (kk * 32u + lane < cnt) {
                     const uint32_t slot = (tail + kk * 32u + lane) & (uint32_t)(SCR_RING - 1);
+#if SA_SCR_L2_HINTS
+                    cp_async4_hint(ring_r + slot, H.pos_table + (rowdelta[rowid & (uint32_t)(SCR_ROWS - 1)] + f0 + lane), pol_stream);
+#else
                     cp_async4(ring_r + slot, H.pos_table + (rowdelta[rowid & (uint32_t)(SCR_ROWS - 1)] + f0 + lane));
+#endif
                     ring_row[slot] = (uint8_t)rowid;
                 }
             }

@@ -7,6 +7,10 @@
 // and buffers that grow on demand instead of a 36-byte-per-MAX_HITS up-front allocation.
 // There is NO CPU fallback: every entry point fails with an SA_ERR_* code if CUDA fails.
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <fstream>
+#include <thread>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -1045,5 +1049,6 @@ size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uin
 }
 
 #include "host_segments.inc"
+#include "host_pipeline.inc"
 
 } // extern "C"
