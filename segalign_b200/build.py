@@ -14,6 +14,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 CSRC = ROOT / "segalign_b200" / "csrc"
 LIB = ROOT / "segalign_b200" / "libsegalign_b200.so"
+CLI = ROOT / "segalign_b200" / "segalign_b200_cli"
 SHIM_OBJ = ROOT / "segalign_b200" / "libsegalign_b200_shim.a"
 ORACLE_DIR = ROOT / "oracle"
 ORACLE_LIB = ORACLE_DIR / "libsa_oracle.so"
@@ -41,7 +42,7 @@ def _newer(target: Path, sources) -> bool:
 
 
 def build_backend(force: bool = False, verbose: bool = False) -> Path:
-    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.inc")) + [ROOT / "include" / "segalign_b200.h"]
+    sources = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted(CSRC.glob("*.inc")) + sorted(CSRC.glob("*.cpp")) + [ROOT / "include" / "segalign_b200.h"]
     if not force and _newer(LIB, sources):
         return LIB
     extra = os.environ.get("SEGALIGN_B200_NVCC_EXTRA", "").split()  # e.g. -DSA_SCR_THREADS=288 (tuning experiments)
@@ -49,6 +50,9 @@ def build_backend(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True, cwd=str(CSRC))
+    # command line front end of the whole-genome driver (host only; links the library by rpath)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(CLI), str(CSRC / "segalign_main.cpp"),
+                    f"-L{LIB.parent}", "-lsegalign_b200", f"-Wl,-rpath,{LIB.parent}"], check=True)
     return LIB
 
 

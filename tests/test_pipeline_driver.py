@@ -132,3 +132,15 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     for c in cmds:
         assert c.startswith("lastz /data/ref.2bit[nameparse=darkspace][multiple][subset=ref_block")
         assert " --format=maf- --ydrop=9430 --gappedthresh=3000 --strand=" in c and " --segments=tmp" in c
+    # the command line front end (segalign_main.cpp) produces the same files
+    import subprocess
+    from segalign_b200.build import CLI
+    out2 = tmp_path / "out_cli"
+    out2.mkdir()
+    backend.ShutdownProcessor()
+    p = subprocess.run([str(CLI), str(tmp_path / "ref.fa"), str(tmp_path / "query.fa"), "/data", f"--out_dir={out2}",
+                        f"--seq_block_size={block_size}", f"--lastz_interval={interval}", f"--wga_chunk={chunk}",
+                        "--num_threads=3", "--nogapped"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert {q.name: q.read_text() for q in out2.glob("*.segments")} == got
+    assert "segment files %d" % len(got) in p.stderr
