@@ -212,7 +212,7 @@ def run_ours(args):
     pinned_np = [p.numpy().view(np.uint64) for p in pinned]
     free_bufs = list(range(nthreads))
     buf_lock = threading.Lock()
-    e2e_bytes = {"h2d": 0, "d2h": 0}
+    e2e_bytes = {"h2d_handed_over": 0, "d2h": 0}
 
     def step_e2e():
         be.ClearQuery(0)
@@ -236,7 +236,7 @@ def run_ours(args):
                 d2h[0] += res.size * 16
             return res.size - 1
         n = sum(pool.map(work, range(len(units))))
-        e2e_bytes["h2d"], e2e_bytes["d2h"] = h2d[0], d2h[0]
+        e2e_bytes["h2d_handed_over"], e2e_bytes["d2h"] = h2d[0], d2h[0]
         return n
 
     def timed(step_fn, steps, warmup):
@@ -352,7 +352,10 @@ def run_ours(args):
                        "host_threads": nthreads, "l2": "256 MB memset between steps; per-step working set >> L2",
                        "parallelism": f"query blocks x{world}, replicated ref+table, no collective"},
             "e2e": {"value": round(e2e_value, 5), "unit": "Gbp/s", "ms_per_step": round(ms_e2e / args.steps, 3),
-                    "h2d_bytes_per_step": int(e2e_bytes["h2d"]), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
+                    "h2d_bytes_per_step": int(st_e2e["h2d_bytes"] // args.steps), "d2h_bytes_per_step": int(e2e_bytes["d2h"]),
+                    "host_bytes_handed_over_per_step": int(e2e_bytes["h2d_handed_over"]),
+                    "note": "the seed vectors handed over are in the seeder's canonical form (exact word + its transition "
+                            "variants per position): the library uploads the base words and rebuilds the vector on the device",
                     "api": "sa_send_query + sa_host_chunk_seeds + sa_seed_and_filter (reference seed-vector ABI)"},
             "gpu_launches": int(st_res["launches"]),
             "roofline": roofline,

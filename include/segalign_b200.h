@@ -195,6 +195,7 @@ typedef struct sa_stats {
     double ms_ref_encode, ms_table_build, ms_query_encode;
     uint64_t launches;         /* kernels launched by this library */
     uint64_t walked;           /* hits the popcount screen left to the tile walk (0 for the tile-walk-only kernels) */
+    uint64_t h2d_bytes;        /* bytes sa_seed_and_filter / sa_send_query actually copied host -> device */
 } sa_stats;
 int sa_get_stats(sa_stats *out);
 int sa_reset_stats(void);

@@ -28,6 +28,23 @@ k_count_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint3
     }
 }
 
+// Seed words from their base words.  The reference's seeder emits, per query position, the exact
+// word followed by its transition variants (src/seeder.cpp:57-74): word[g*per + v] = base[g] ^ xm[v].
+// When the host finds a seed vector in that form it uploads only the base words (1/per of the
+// bytes) and this kernel rebuilds the vector in HBM, bit for bit.
+struct VariantMasks {
+    uint64_t xm[32]; // xm[0] = 0; xm[v] = (TRANSITION_MASK << 2*t_v) << 32
+};
+__global__ void __launch_bounds__(256)
+k_expand_bases(const uint64_t *__restrict__ bases, uint32_t num_seeds, uint32_t per, VariantMasks M,
+               uint64_t *__restrict__ seeds) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < num_seeds; s += stride) {
+        const uint32_t g = s / per, v = s - g * per;
+        seeds[s] = __ldg(bases + g) ^ M.xm[v];
+    }
+}
+
 __device__ __forceinline__ uint32_t lower_bound_dev(const uint32_t *a, uint32_t n, uint32_t v) {
     uint32_t lo = 0, hi = n;
     while (lo < hi) {

@@ -109,6 +109,8 @@ struct Workspace {
     uint8_t *d_temp = nullptr; size_t temp_cap = 0;
     uint32_t *d_flags = nullptr; size_t flags_cap = 0;
     uint32_t *d_excl = nullptr; size_t excl_cap = 0;
+    uint64_t *h_bases = nullptr; size_t h_bases_cap = 0; // pinned: base seed words of a canonical seed vector
+    uint64_t *d_bases = nullptr; size_t d_bases_cap = 0;
     uint32_t *h_small = nullptr; // pinned, 64 words: [0..15] counters, [16..19] plan, [20] seed count staging
     sa_segment *h_out = nullptr; // pinned staging for the first FINALIZE_CAP result records
 };
@@ -145,6 +147,7 @@ struct Global {
     int extend_grid = 0;
     int wide_grid = 0;         // k_extend_wide (warp per hit), SEGALIGN_B200_WIDE=0 sends all survivors to k_extend_hits
     bool use_wide = true;
+    bool use_compact = true;   // SEGALIGN_B200_COMPACT_SEEDS=0: always copy seed vectors as they are
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
     uint32_t query_len[SA_BUFFER_DEPTH] = {};
@@ -280,6 +283,8 @@ void destroy_workspace(Workspace *w) {
     cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_surv2); cudaFree(w->d_dedup); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
+    if (w->h_bases) cudaFreeHost(w->h_bases);
+    cudaFree(w->d_bases);
     cudaFreeHost(w->h_out);
     for (auto &e : w->ev) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
@@ -705,6 +710,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         G.wide_grid = 4 * std::max(1, sms);   // four-warp blocks, one warp per hit
         if (const char *e = getenv("SEGALIGN_B200_WIDE_CTAS")) if (atoi(e) > 0) G.wide_grid = atoi(e) * std::max(1, sms);
         { const char *e = getenv("SEGALIGN_B200_WIDE"); G.use_wide = !(e && atoi(e) == 0); }
+        { const char *e = getenv("SEGALIGN_B200_COMPACT_SEEDS"); G.use_compact = !(e && atoi(e) == 0); }
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
         for (SeqPlanes *p : all)
@@ -881,6 +887,7 @@ int sa_send_query(const char *query_base, size_t start_addr, uint32_t len, uint3
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         std::lock_guard<std::mutex> l(G.stats_mu);
         G.stats.ms_query_encode += ms;
+        G.stats.h2d_bytes += len;
     }
     G.query_loaded[buffer] = true;
     return SA_OK;
@@ -918,7 +925,44 @@ int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint3
     pt.mark(PH_START);
     TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
     TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
-    CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    // A seed vector in the seeder's own form (per position: exact word, then its transition variants,
+    // src/seeder.cpp:57-74) is uploaded as its base words only and rebuilt on the device; any other
+    // vector is copied as it is.  One pass over the caller's vector either way.
+    const uint32_t per = 1u + (G.transition ? (uint32_t)G.shape.num_trans : 0u);
+    bool compact = G.use_compact && per > 1 && num_seeds >= 4096 && num_seeds % per == 0;
+    if (compact) {
+        const uint32_t groups = num_seeds / per;
+        if (w->h_bases_cap < groups) {
+            if (w->h_bases) cudaFreeHost(w->h_bases);
+            w->h_bases = nullptr; w->h_bases_cap = 0;
+            const size_t cap = std::max<size_t>(groups, G.max_seeds / per + 1);
+            CU(cudaMallocHost((void **)&w->h_bases, cap * sizeof(uint64_t)), SA_ERR_MALLOC);
+            w->h_bases_cap = cap;
+        }
+        VariantMasks VM = {};
+        for (uint32_t v = 1; v < per; v++) VM.xm[v] = (uint64_t)(2u << (2 * G.shape.tvar[v - 1])) << 32;
+        uint64_t bad = 0;
+        for (uint32_t gi = 0; gi < groups && !bad; gi++) {
+            const uint64_t *p = seeds + (size_t)gi * per;
+            const uint64_t base = p[0];
+            for (uint32_t v = 1; v < per; v++) bad |= p[v] ^ base ^ VM.xm[v];
+            w->h_bases[gi] = base;
+        }
+        compact = bad == 0;
+        if (compact) {
+            TRY(ensure(w->d_bases, w->d_bases_cap, groups, "seed_bases"));
+            CU(cudaMemcpyAsync(w->d_bases, w->h_bases, (size_t)groups * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+            k_expand_bases<<<grid_for(num_seeds, 256), 256, 0, w->stream>>>(w->d_bases, num_seeds, per, VM, w->d_seeds);
+            std::lock_guard<std::mutex> l(G.stats_mu);
+            G.stats.h2d_bytes += (uint64_t)groups * sizeof(uint64_t);
+            G.stats.launches += 1;
+        }
+    }
+    if (!compact) {
+        CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        G.stats.h2d_bytes += (uint64_t)num_seeds * sizeof(uint64_t);
+    }
     w->h_small[20] = num_seeds; // pinned: the seed count travels to d_plan[2] on the stream
     CU(cudaMemcpyAsync(w->d_plan + 2, w->h_small + 20, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
     pt.mark(PH_SEEDS);

@@ -74,6 +74,51 @@ def test_lane_pair_exact_kernel_alone_matches_reference_golden(backend, case, mo
     H.assert_calls_equal(got, want, "lane-pair exact kernel alone vs reference golden")
 
 
+@pytest.mark.parametrize("name", ["diverged_default", "masked_multichrom", "repeats_entropy"])
+def test_plain_seed_vector_copy_matches_reference_golden(backend, name, monkeypatch):
+    """SEGALIGN_B200_COMPACT_SEEDS=0: the seed vector is copied as handed over instead of as base
+    words + device-side rebuild of the transition variants."""
+    monkeypatch.setenv("SEGALIGN_B200_COMPACT_SEEDS", "0")
+    case = H.CASES_BY_NAME[name]
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case)
+    H.assert_calls_equal(got, want, "plain seed vector copy vs reference golden")
+
+
+def test_non_canonical_seed_vectors_match_cpu_oracle(backend):
+    """Seed vectors that are NOT in the seeder's form (shuffled words, a truncated vector, words of one
+    variant only) must take the plain copy and still give what the oracle gives for the same vector."""
+    from oracle import sa_oracle_py as sao
+    case = H.CASES_BY_NAME["diverged_default"]
+    ref, query = case.inputs()
+    span, _ = H.setup_backend(backend, case, ref, query)
+    shape = sao.Shape(case.seed_shape)
+    table = sao.Table(shape, ref, ref.size, case.step)
+    ref_enc = sao.encode(ref)
+    q_fwd, _ = sao.encode_rc(query)
+    params = sao.make_params(H.matrix_for(case), case.xdrop, case.hspthresh, case.noentropy, shape.span, 748058112)
+    seeds = shape.chunk_seeds(query, 0, min(60_000, query.size - span), case.transition)
+    assert seeds.size % 13 == 0 and seeds.size > 13 * 4096
+    rng = np.random.default_rng(9)
+    variants = {"shuffled": rng.permutation(seeds), "truncated": seeds[:-5], "one_variant": seeds[3::13].copy(),
+                "swapped_pair": np.concatenate([seeds[:13][::-1], seeds[13:]])}
+    backend.reset_stats()
+    for tag, vec in variants.items():
+        vec = np.ascontiguousarray(vec)
+        want = sao.seed_and_filter(params, table, ref_enc, q_fwd, vec)
+        got = backend.SeedAndFilter(vec, False, 0)
+        assert got[0]["len"] == want[0]["len"] and got[0]["score"] == want[0]["score"], tag
+        assert np.array_equal(got[1:], want[1:]), tag
+    # none of them may have gone through the compact upload
+    assert backend.stats()["h2d_bytes"] == sum(v.size * 8 for v in variants.values())
+    # ... while the canonical vector does
+    backend.reset_stats()
+    want = sao.seed_and_filter(params, table, ref_enc, q_fwd, seeds)
+    got = backend.SeedAndFilter(seeds, False, 0)
+    assert np.array_equal(got[1:], want[1:])
+    assert backend.stats()["h2d_bytes"] == seeds.size * 8 // 13
+
+
 def test_screen_decides_most_random_hits(backend):
     """The popcount screen (default kernel) must be live -- few hits reach the tile walk on a
     diverged random pair -- and the tile-walk-only kernel must report none."""
