@@ -35,6 +35,9 @@ namespace sa {
 #ifndef SA_SCR_Q_CAP
 #define SA_SCR_Q_CAP 96
 #endif
+#ifndef SA_SCR_REQ_LANES
+#define SA_SCR_REQ_LANES 6 // lanes that fetch the six records of one hit (6 or 2)
+#endif
 #ifndef SA_SCR_L2_HINTS
 #define SA_SCR_L2_HINTS 1 // reference records evict_last, seed positions evict_first (keeps the records L2-resident)
 #endif
@@ -170,6 +173,29 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     // reference records w-3 .. w+2 of n staged hits starting at ring position `from`: six
     // neighbouring lanes per hit, 16 bytes each, straight into the staging buffer
     auto request_records = [&](uint32_t from, uint32_t n) {
+#if SA_SCR_REQ_LANES == 2 || SA_SCR_REQ_LANES == 1
+        // L lanes per hit, 6/L consecutive records each: more L1 tag lookups than the six-lane mapping
+        // below (a 32-lane request touches more lines), a fraction of its address arithmetic
+        constexpr uint32_t L = SA_SCR_REQ_LANES, PER = SCREEN_RECS / L, HITS = 32u / L;
+        const uint32_t part = (lane % L) * PER;
+#pragma unroll
+        for (uint32_t pass = 0; pass < L; pass++) {
+            const uint32_t hs = pass * HITS + lane / L;
+            if (hs < n) {
+                const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)] + H.seed_size;
+                const uint4 *src = rrec_m3 + ((r >> 5) + part);
+                uint4 *dst = stage + hs * SCR_STAGE_STRIDE + part;
+#pragma unroll
+                for (uint32_t j = 0; j < PER; j++) {
+#if SA_SCR_L2_HINTS
+                    cp_async16_hint(dst + j, src + j, pol_keep);
+#else
+                    cp_async16(dst + j, src + j);
+#endif
+                }
+            }
+        }
+#else
 #pragma unroll
         for (uint32_t i = 0; i < SCREEN_RECS; i++) {
             const uint32_t f = i * 32u + lane;
@@ -183,6 +209,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
 #endif
             }
         }
+#endif
     };
 
     for (;;) {
