@@ -119,6 +119,28 @@ def test_non_canonical_seed_vectors_match_cpu_oracle(backend):
     assert backend.stats()["h2d_bytes"] == seeds.size * 8 // 13
 
 
+@pytest.mark.parametrize("n_ref,n_query,off", [(64, 40, 3), (257, 64, 100), (1000, 333, 0), (5000, 20, 4000),
+                                                (4097, 4097, 0), (100_000, 96, 99_904), (100_000, 700, 0)])
+@pytest.mark.parametrize("device_seeding", [False, True], ids=["vector", "range"])
+def test_tiny_and_ragged_blocks_match_cpu_oracle(backend, n_ref, n_query, off, device_seeding):
+    """Blocks far smaller than the screen's 160-cell window, queries that end at the block end, a
+    query of one seed span + 1: every window then runs into the terminator padding on one or both
+    sides.  The query is a (lightly mutated, partly soft-masked) slice of the reference so that the
+    calls do have hits."""
+    from segalign_b200 import genome
+    rng = np.random.default_rng(n_ref * 7 + n_query)
+    ref = genome.random_genome(n_ref, rng)
+    query = genome.mutate(ref[off:off + n_query].copy(), 0.05, rng)
+    if n_query > 200:
+        query = genome.soft_mask(query, 0.1, rng, mean_run=20)
+    H.GENERATORS["_tiny"] = lambda _rng: (ref, query)
+    case = H.Case(f"tiny_{n_ref}_{n_query}", "_tiny", hspthresh=1500 if n_query < 100 else 3000, wga_chunk=300)
+    want = H.run_cpu_oracle(case, ref, query, max_hits_device=748058112)
+    got = H.run_backend(backend, case, ref, query, device_seeding=device_seeding)
+    H.assert_calls_equal(got, want, "tiny / ragged blocks vs cpu oracle")
+    assert sum(w[4].size - 1 for w in want) > 0 or n_query <= 64
+
+
 def test_screen_decides_most_random_hits(backend):
     """The popcount screen (default kernel) must be live -- few hits reach the tile walk on a
     diverged random pair -- and the tile-walk-only kernel must report none."""
