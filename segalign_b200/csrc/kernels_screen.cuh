@@ -33,7 +33,7 @@ namespace sa {
 #define SA_SCR_STAGE_STRIDE 7
 #endif
 #ifndef SA_SCR_Q_CAP
-#define SA_SCR_Q_CAP 96
+#define SA_SCR_Q_CAP 64
 #endif
 #ifndef SA_SCR_REQ_LANES
 #define SA_SCR_REQ_LANES 6 // lanes that fetch the six records of one hit (6 or 2)
@@ -62,7 +62,7 @@ constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STA
 constexpr size_t SCR_OFF_RING = SCR_OFF_ROWS + (size_t)SCR_WARPS * SCR_ROWS * SCR_ROW_STRIDE * 4;
 constexpr size_t SCR_OFF_QUEUE = SCR_OFF_RING + (size_t)SCR_WARPS * SCR_RING * 4;
 constexpr size_t SCR_OFF_RROW = SCR_OFF_QUEUE + (size_t)SCR_WARPS * SCR_Q_CAP * 8;
-constexpr size_t SCR_OFF_DELTA = SCR_OFF_RROW + (size_t)SCR_WARPS * SCR_RING;
+constexpr size_t SCR_OFF_DELTA = SCR_OFF_RROW + (size_t)SCR_WARPS * SCR_RING * 2;
 constexpr size_t SCR_SMEM_BYTES = SCR_OFF_DELTA + (size_t)SCR_WARPS * SCR_ROWS * 4;
 static_assert((SCR_SMEM_BYTES + 1024) * SA_SCR_MIN_CTAS <= 233472, "k_filter_hits3: shared memory of the resident blocks exceeds an SM");
 static_assert(SCR_Q_DRAIN >= 1 && SCR_Q_CAP >= SCR_Q_DRAIN + 31, "a round may queue 32 hits after the drain threshold was missed");
@@ -145,15 +145,22 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem + SCR_OFF_ROWS) + warp * SCR_ROWS * SCR_ROW_STRIDE;
     uint32_t *ring_r = reinterpret_cast<uint32_t *>(smem + SCR_OFF_RING) + warp * SCR_RING;
     uint32_t *myq = reinterpret_cast<uint32_t *>(smem + SCR_OFF_QUEUE) + warp * SCR_Q_CAP * 2;
-    uint8_t *ring_row = reinterpret_cast<uint8_t *>(smem + SCR_OFF_RROW) + warp * SCR_RING;
-    uint32_t *rowdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS; // bucket start - exclusive hit prefix, per row
+    uint16_t *ring_meta = reinterpret_cast<uint16_t *>(smem + SCR_OFF_RROW) + warp * SCR_RING; // row id | variant << 8, per staged hit
+    // per owner (seed word with hits) of the bucket set being expanded: bucket start - exclusive hit
+    // prefix, and (device seeding) the row id of its query position
+    uint32_t *ownerdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS;
+    uint8_t *ownerrow = reinterpret_cast<uint8_t *>(ownerdelta + 32);
     const uint4 *rrec_m3 = P.rrec - 3; // record w-3 of a window (REC_FRONT >= 3 records of front padding)
 #if SA_SCR_L2_HINTS
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #endif
 
-    const uint32_t total_items = H.num_items;
+    const uint32_t n_var = SRC == SRC_RANGE ? H.per : 1u;       // bucket sets per group (device seeding: 1 + transition variants)
+    const uint32_t n_units = SRC == SRC_RANGE ? H.num_items / n_var : H.num_items; // query positions / seed words
     uint32_t key_base = 0, g_total = 0, g_done = 0, g_row_base = 0;
+    uint32_t v_cur = 0, v_next = n_var, valid_mask = 0; // device seeding: variant of the current set, lanes with a valid position
+    uint32_t lane_kmer = 0;        // lane: exact k-mer of its query position (device seeding)
+    bool lane_valid = false;
     uint32_t head = 0, tail = 0;   // hit ring: [head, tail) staged and not yet screened (monotonic counters)
     uint32_t next_c = 0;           // lane 0: the next group number, fetched one refill ahead
     if (lane == 0) next_c = atomicAdd(counters + CTR_CHUNK, 1u);
@@ -216,46 +223,77 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
         // ---------------- refill the hit ring
         const uint32_t tail_prev = tail; // positions below this were copied in by an earlier refill
         while (tail - head < (uint32_t)SCR_REFILL && !exhausted) {
-            const bool new_group = g_done == g_total;
-            if (new_group) {
+            // A "bucket set" = 32 buckets, one per lane, expanded together.  Seed vectors (SRC_SEEDS): the
+            // buckets of 32 consecutive seed words.  Device seeding (SRC_RANGE): the buckets of ONE
+            // variant (exact word, or the transition at one care position) of 32 consecutive query
+            // positions -- window, k-mer and aligned query row are then computed once per position
+            // instead of once per seed word, and the index lookups of a set are independent loads.
+            const bool new_set = g_done == g_total;
+            if (new_set && (SRC == SRC_SEEDS || v_next == n_var)) {
                 // a new group may take up to 32 rows: the rows of the unscreened hits must survive
                 if (tail != head) {
-                    const uint32_t live = (row_tail - ring_row[head & (SCR_RING - 1)]) & 0xFFu;
+                    const uint32_t live = (row_tail - (ring_meta[head & (SCR_RING - 1)] & 0xFFu)) & 0xFFu;
                     if (live > (uint32_t)(SCR_ROWS - 32)) break; // then more than 32 hits are staged: screen first
                 }
                 const uint32_t c = __shfl_sync(0xFFFFFFFFu, next_c, 0);
                 const unsigned long long start = (unsigned long long)c * 32u;
-                if (start >= total_items) { exhausted = true; break; }
+                if (start >= n_units) { exhausted = true; break; }
                 if (lane == 0) next_c = atomicAdd(counters + CTR_CHUNK, 1u);
                 key_base = (uint32_t)start;
-                g_done = 0;
+                if (SRC == SRC_RANGE) {
+                    // this lane's query position: validity, exact k-mer, aligned row
+                    const uint32_t pi = key_base + lane;
+                    lane_valid = false; lane_kmer = 0;
+                    uint32_t qa = 0;
+                    if (pi < n_units) {
+                        const uint32_t qpos = H.j0 + pi;
+                        uint64_t W; uint32_t Tw, Sw;
+                        load_window(P.qrec, (int)qpos, W, Tw, Sw);
+                        const uint32_t span_mask = H.shape.span >= 32 ? 0xFFFFFFFFu : ((1u << H.shape.span) - 1u);
+                        lane_valid = ((Tw | Sw) & span_mask) == 0; // all span cells upper-case ACGT (ntcoding.cpp:47-52)
+                        for (int i = 0; i < H.shape.weight; i++) lane_kmer = (lane_kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
+                        qa = qpos + H.seed_size;
+                    }
+                    valid_mask = __ballot_sync(0xFFFFFFFFu, lane_valid);
+                    acc_seeds += __popc(valid_mask) * n_var;
+                    g_row_base = row_tail;
+                    if (lane_valid) {
+                        const uint4 *qr = P.qrec + (int)(qa >> 5) - 3;
+                        const ScreenRec a[SCREEN_RECS] = {as_rec(__ldg(qr)), as_rec(__ldg(qr + 1)), as_rec(__ldg(qr + 2)),
+                                                          as_rec(__ldg(qr + 3)), as_rec(__ldg(qr + 4)), as_rec(__ldg(qr + 5))};
+                        uint32_t row[SCREEN_ROW_WORDS];
+                        screen_align(a, qa & 31u, row);
+                        const uint32_t slot = (row_tail + __popc(valid_mask & lt_mask)) & (uint32_t)(SCR_ROWS - 1);
+                        uint4 *dst = reinterpret_cast<uint4 *>(rows + slot * SCR_ROW_STRIDE);
+                        dst[0] = make_uint4(row[0], row[1], row[2], row[3]);
+                        dst[1] = make_uint4(row[4], row[5], row[6], row[7]);
+                        dst[2] = make_uint4(row[8], row[9], row[10], pi * n_var); // word 11 = seed order index of the exact word
+                    }
+                    row_tail += __popc(valid_mask);
+                    v_next = valid_mask ? 0u : n_var; // a group without a valid position has no bucket sets
+                    if (!valid_mask) continue;
+                }
             }
-            // this lane's seed word and bucket (recomputed when a group is staged in several parts)
-            const uint32_t k = key_base + lane;
+            if (SRC == SRC_RANGE && new_set) v_cur = v_next++;
+            // this lane's bucket of the set (recomputed when a set is staged in several parts)
             uint32_t b_start = 0, n = 0, qa = 0;
             bool valid = false;
-            if (k < total_items) {
-                uint32_t kmer = 0, qpos = 0;
-                if (SRC == SRC_SEEDS) {
+            if (SRC == SRC_SEEDS) {
+                const uint32_t k = key_base + lane;
+                if (k < n_units) {
                     const uint64_t word = __ldg(H.seeds + k);
-                    kmer = (uint32_t)(word >> 32); qpos = (uint32_t)word;
+                    const uint32_t kmer = (uint32_t)(word >> 32);
                     valid = true;
-                } else {
-                    const uint32_t pi = k / H.per, v = k - pi * H.per;
-                    qpos = H.j0 + pi;
-                    uint64_t W; uint32_t Tw, Sw;
-                    load_window(P.qrec, (int)qpos, W, Tw, Sw);
-                    const uint32_t span_mask = H.shape.span >= 32 ? 0xFFFFFFFFu : ((1u << H.shape.span) - 1u);
-                    valid = ((Tw | Sw) & span_mask) == 0; // all span cells upper-case ACGT (ntcoding.cpp:47-52)
-                    for (int i = 0; i < H.shape.weight; i++) kmer = (kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
-                    if (v > 0) kmer ^= 2u << (2 * H.shape.tvar[v - 1]); // seeder.cpp:64-71
-                }
-                if (valid) {
                     const uint32_t b_end = __ldg(H.index_table + kmer);
                     b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
                     n = b_end - b_start;
-                    qa = qpos + H.seed_size;
+                    qa = (uint32_t)word + H.seed_size;
                 }
+            } else if (lane_valid) {
+                const uint32_t kmer = v_cur ? lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur - 1])) : lane_kmer; // seeder.cpp:64-71
+                const uint32_t b_end = __ldg(H.index_table + kmer);
+                b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                n = b_end - b_start;
             }
             uint32_t incl = n;
 #pragma unroll
@@ -265,48 +303,61 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             }
             const uint32_t excl = incl - n;
             const unsigned with_hits = __ballot_sync(0xFFFFFFFFu, n > 0);
-            if (new_group) {
+            if (new_set) {
+                g_done = 0;
                 g_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 acc_hits += g_total;
-                acc_seeds += __popc(__ballot_sync(0xFFFFFFFFu, valid));
-                if (with_hits) { acc_last = key_base + (31u - __clz(with_hits)); any_hits = true; } // groups come in ascending order per warp
-                if (g_total == 0) continue;
-                // aligned query window of every seed word that has hits (shared by all its hits)
-                g_row_base = row_tail;
-                if (n > 0) {
-                    const uint4 *qr = P.qrec + (int)(qa >> 5) - 3;
-                    const ScreenRec a[SCREEN_RECS] = {as_rec(__ldg(qr)), as_rec(__ldg(qr + 1)), as_rec(__ldg(qr + 2)),
-                                                      as_rec(__ldg(qr + 3)), as_rec(__ldg(qr + 4)), as_rec(__ldg(qr + 5))};
-                    uint32_t row[SCREEN_ROW_WORDS];
-                    screen_align(a, qa & 31u, row);
-                    const uint32_t slot = (row_tail + __popc(with_hits & lt_mask)) & (uint32_t)(SCR_ROWS - 1);
-                    uint4 *dst = reinterpret_cast<uint4 *>(rows + slot * SCR_ROW_STRIDE);
-                    dst[0] = make_uint4(row[0], row[1], row[2], row[3]);
-                    dst[1] = make_uint4(row[4], row[5], row[6], row[7]);
-                    dst[2] = make_uint4(row[8], row[9], row[10], k); // word 11 = seed order index of the row
-                    rowdelta[slot] = b_start - excl; // hit f of the group sits at pos_table[f + this]
+                if (SRC == SRC_SEEDS) acc_seeds += __popc(__ballot_sync(0xFFFFFFFFu, valid));
+                if (with_hits) { // seed order index of the last hit-bearing seed word seen by this warp
+                    const uint32_t top = key_base + (31u - __clz(with_hits));
+                    acc_last = max(acc_last, SRC == SRC_SEEDS ? top : top * n_var + v_cur);
+                    any_hits = true;
                 }
-                row_tail += __popc(with_hits);
+                if (g_total == 0) continue;
+                if (SRC == SRC_SEEDS) {
+                    // aligned query window of every seed word that has hits (shared by all its hits)
+                    g_row_base = row_tail;
+                    if (n > 0) {
+                        const uint4 *qr = P.qrec + (int)(qa >> 5) - 3;
+                        const ScreenRec a[SCREEN_RECS] = {as_rec(__ldg(qr)), as_rec(__ldg(qr + 1)), as_rec(__ldg(qr + 2)),
+                                                          as_rec(__ldg(qr + 3)), as_rec(__ldg(qr + 4)), as_rec(__ldg(qr + 5))};
+                        uint32_t row[SCREEN_ROW_WORDS];
+                        screen_align(a, qa & 31u, row);
+                        const uint32_t slot = (row_tail + __popc(with_hits & lt_mask)) & (uint32_t)(SCR_ROWS - 1);
+                        uint4 *dst = reinterpret_cast<uint4 *>(rows + slot * SCR_ROW_STRIDE);
+                        dst[0] = make_uint4(row[0], row[1], row[2], row[3]);
+                        dst[1] = make_uint4(row[4], row[5], row[6], row[7]);
+                        dst[2] = make_uint4(row[8], row[9], row[10], key_base + lane); // word 11 = seed order index of the row
+                    }
+                    row_tail += __popc(with_hits);
+                }
+            }
+            // owner tables of this set: the j-th lane with hits -> position-table offset and row id
+            if (n > 0) {
+                const uint32_t j = __popc(with_hits & lt_mask);
+                ownerdelta[j] = b_start - excl; // hit f of the set sits at pos_table[f + this]
+                ownerrow[j] = (uint8_t)(g_row_base + (SRC == SRC_SEEDS ? j : __popc(valid_mask & lt_mask)));
             }
             const uint32_t cnt = min(g_total - g_done, (uint32_t)SCR_RING - (tail - head));
+            const uint32_t vtag = SRC == SRC_RANGE ? v_cur << 8 : 0u;
             __syncwarp();
             for (uint32_t kk = 0; kk * 32u < cnt; kk++) {
-                // owner of hit f = the j-th seed word with hits, j = #{words with hits whose inclusive
-                // prefix is <= f}: one ballot for the 32 hits' common base, one OR-reduction of the
-                // prefix boundaries that fall inside these 32 hits, one popcount per lane
+                // owner of hit f = the j-th lane with hits, j = #{lanes with hits whose inclusive prefix is
+                // <= f}: one ballot for the 32 hits' common base, one OR-reduction of the prefix
+                // boundaries that fall inside these 32 hits, one popcount per lane
                 const uint32_t f0 = g_done + kk * 32u;
                 const uint32_t j0 = __popc(__ballot_sync(0xFFFFFFFFu, n > 0 && incl <= f0));
                 const uint32_t bp = incl - f0 - 1u;
                 const uint32_t bounds = __reduce_or_sync(0xFFFFFFFFu, (n > 0 && incl > f0 && bp < 32u) ? 1u << bp : 0u);
-                const uint32_t rowid = g_row_base + j0 + __popc(bounds & lt_mask);
+                const uint32_t j = j0 + __popc(bounds & lt_mask);
                 if (kk * 32u + lane < cnt) {
                     const uint32_t slot = (tail + kk * 32u + lane) & (uint32_t)(SCR_RING - 1);
 #if SA_SCR_L2_HINTS
-                    cp_async4_hint(ring_r + slot, H.pos_table + (rowdelta[rowid & (uint32_t)(SCR_ROWS - 1)] + f0 + lane), pol_stream);
+                    cp_async4_hint(ring_r + slot, H.pos_table + (ownerdelta[j] + f0 + lane), pol_stream);
 #else
-                    cp_async4(ring_r + slot, H.pos_table + (rowdelta[rowid & (uint32_t)(SCR_ROWS - 1)] + f0 + lane));
+                    cp_async4(ring_r + slot, H.pos_table + (ownerdelta[j] + f0 + lane));
 #endif
-                    ring_row[slot] = (uint8_t)rowid;
+                    ring_meta[slot] = (uint16_t)(ownerrow[j] | vtag);
                 }
             }
             __syncwarp();
@@ -332,15 +383,16 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 cp_async_wait_group<1>(); // everything but this refill's positions has landed
             }
             const bool have = lane < n1;
-            uint32_t r0 = 0, rowid = 0;
+            uint32_t r0 = 0, rowid = 0, vkey = 0;
             if (have) {
-                const uint32_t slot = (head + lane) & (uint32_t)(SCR_RING - 1);
-                rowid = ring_row[slot];
+                const uint32_t meta = ring_meta[(head + lane) & (uint32_t)(SCR_RING - 1)];
+                rowid = meta & 0xFFu;
+                vkey = meta >> 8;
             }
             const uint4 *qrow = reinterpret_cast<const uint4 *>(rows + (rowid & (uint32_t)(SCR_ROWS - 1)) * SCR_ROW_STRIDE);
             const uint4 q_a = qrow[0], q_b = qrow[1], q_c = qrow[2];
             const uint32_t qr[SCREEN_ROW_WORDS] = {q_a.x, q_a.y, q_a.z, q_a.w, q_b.x, q_b.y, q_b.z, q_b.w, q_c.x, q_c.y, q_c.z, 0u};
-            const uint32_t key = q_c.w;
+            const uint32_t key = q_c.w + vkey; // seed order index of the hit's seed word
             __syncwarp();
             if (have) r0 = ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size;
             uint32_t rr[SCREEN_ROW_WORDS];
