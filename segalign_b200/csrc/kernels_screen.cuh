@@ -160,7 +160,6 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t key_base = 0, g_total = 0, g_done = 0, g_row_base = 0;
     uint32_t v_cur = 0, v_next = n_var, valid_mask = 0; // device seeding: variant of the current set, lanes with a valid position
     uint32_t lane_kmer = 0;        // lane: exact k-mer of its query position (device seeding)
-    uint32_t pf_end = 0, pf_start = 0, pf_for = 0xFFFFFFFFu; // lane: index entries of set pf_for, requested one set ahead
     bool lane_valid = false;
     uint32_t head = 0, tail = 0;   // hit ring: [head, tail) staged and not yet screened (monotonic counters)
     uint32_t next_c = 0;           // lane 0: the next group number, fetched one refill ahead
@@ -272,7 +271,6 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     }
                     row_tail += __popc(valid_mask);
                     v_next = valid_mask ? 0u : n_var; // a group without a valid position has no bucket sets
-                    pf_for = 0xFFFFFFFFu;
                     if (!valid_mask) continue;
                 }
             }
@@ -291,25 +289,11 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     n = b_end - b_start;
                     qa = (uint32_t)word + H.seed_size;
                 }
-            } else {
-                // the index entries of a set were requested while the previous set of the group was being
-                // expanded (pf_*); only the first set of a group and re-visits of a set load them here
-                uint32_t b_end = pf_end;
-                b_start = pf_start;
-                if (lane_valid && !(new_set && pf_for == v_cur)) {
-                    const uint32_t kmer = v_cur ? lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur - 1])) : lane_kmer; // seeder.cpp:64-71
-                    b_end = __ldg(H.index_table + kmer);
-                    b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
-                }
-                n = lane_valid ? b_end - b_start : 0u;
-                if (new_set) {
-                    pf_for = v_next;
-                    if (lane_valid && v_next < n_var) {
-                        const uint32_t kmer = lane_kmer ^ (2u << (2 * H.shape.tvar[v_next - 1]));
-                        pf_end = __ldg(H.index_table + kmer);
-                        pf_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
-                    }
-                }
+            } else if (lane_valid) {
+                const uint32_t kmer = v_cur ? lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur - 1])) : lane_kmer; // seeder.cpp:64-71
+                const uint32_t b_end = __ldg(H.index_table + kmer);
+                b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                n = b_end - b_start;
             }
             uint32_t incl = n;
 #pragma unroll
