@@ -333,6 +333,21 @@ def run_ours(args):
     assert st_acct["hits"] == st_probe["hits"] and st_acct["hsps"] == st_probe["hsps"]
     ext_cells_probe = st_acct["ext_cells"]
     ext_per_hit = ext_cells_probe / max(1, st_acct["hits"])
+    # DRAM traffic of the dominant kernel per launch: from the committed `ncu --set full` capture of
+    # this same command line (profiles/*_k_filter_hits3_ncu_summary.txt; bench.py never runs under ncu)
+    traffic, traffic_src = None, None
+    if prev_kernel == 3:
+        caps = sorted((ROOT / "profiles").glob("*_k_filter_hits3_ncu_summary.txt"))
+        if caps:
+            tot, n_cap = 0.0, 0
+            for line in caps[-1].read_text().splitlines():
+                if line.startswith("dram__bytes_read.sum") or line.startswith("dram__bytes_write.sum"):
+                    unit = line.split()[1]
+                    vals = [float(x) for x in line[line.index("["):].strip("[]").replace("'", "").split(",")]
+                    tot += sum(vals) / len(vals) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+                    n_cap += 1
+            if n_cap == 2:
+                traffic, traffic_src = round(tot), "profiles/" + caps[-1].name
     peaks = {}
     pk = ROOT / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -352,7 +367,7 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": round(alg_bytes / n_launch),
                 "avg_launch_ms": round(st_probe["ms_prefilter"] / n_launch, 4), "launches": n_launch,
                 "measured": "serialized pass of %d launches after the timed region (CUDA events on the kernel's stream)" % n_launch,
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "bytes_formula": "16*S + 4*H (seed lookup, fused into this kernel) + 64*H + E (extension), per rank; "
                                  "E counted by an untimed pass of the tile-walk-only kernel over the same units",
                 "filter_kernel": int(prev_kernel),
