@@ -41,6 +41,7 @@ import sys
 import tempfile
 import threading
 import time
+import zlib
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
@@ -201,13 +202,25 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # checksum of checksums over the HSP records of one step (order-independent over the units): the
+    # three legs must return the same bytes at full size
+    step_crc = {}
+
+    def unit_crc(u, res):
+        return (zlib.crc32(res[1:].tobytes()) * (2 * u + 1)) & 0xFFFFFFFFFFFF
+
     # ---- leg 1: resident inputs, device seeding -------------------------------------------
     def step_resident():
+        crcs = [0] * len(units)
+
         def work(u):
             rev, j0, j1 = units[u]
             res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
+            crcs[u] = unit_crc(u, res)
             return res.size - 1
-        return sum(pool.map(work, range(len(units))))
+        n = sum(pool.map(work, range(len(units))))
+        step_crc["resident"] = sum(crcs) & 0xFFFFFFFFFFFFFFFF
+        return n
 
     # ---- leg 2: reference ABI with host buffers ------------------------------------------
     max_words = genome.DEFAULT_WGA_CHUNK * 13
@@ -221,6 +234,7 @@ def run_ours(args):
         be.ClearQuery(0)
         be.SendQueryWriteRequest(query, 0, query.size, 0)   # pageable host ASCII -> HBM, as main.cpp:661
         h2d, d2h = [query.size], [0]
+        crcs = [0] * len(units)
 
         def work(u):
             rev, j0, j1 = units[u]
@@ -234,12 +248,14 @@ def run_ours(args):
             finally:
                 with buf_lock:
                     free_bufs.append(b)
+            crcs[u] = unit_crc(u, res)
             with buf_lock:
                 h2d[0] += seeds.size * 8
                 d2h[0] += res.size * 16
             return res.size - 1
         n = sum(pool.map(work, range(len(units))))
         e2e_bytes["h2d_handed_over"], e2e_bytes["d2h"] = h2d[0], d2h[0]
+        step_crc["vector_abi"] = sum(crcs) & 0xFFFFFFFFFFFFFFFF
         return n
 
     # ---- leg 3: the library's own driver path with host buffers (what sa_pipeline_run does per query
@@ -254,15 +270,18 @@ def run_ours(args):
         be.ClearQuery(0)
         be.SendQueryWriteRequest(query_pinned_np, 0, query.size, 0)
         d2h = [0]
+        crcs = [0] * len(units)
 
         def work(u):
             rev, j0, j1 = units[u]
             res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
+            crcs[u] = unit_crc(u, res)
             with buf_lock:
                 d2h[0] += res.size * 16
             return res.size - 1
         n = sum(pool.map(work, range(len(units))))
         range_d2h[0] = d2h[0]
+        step_crc["e2e"] = sum(crcs) & 0xFFFFFFFFFFFFFFFF
         return n
 
     def timed(step_fn, steps, warmup):
@@ -296,6 +315,7 @@ def run_ours(args):
     assert hsps_e2e == hsps_res, f"e2e path returned {hsps_e2e} HSPs, resident path {hsps_res}"
     ms_e2r, wall_e2r, hsps_e2r, st_e2r = timed(step_e2e_range, args.steps, max(1, args.warmup // 3))
     assert hsps_e2r == hsps_res, f"range e2e path returned {hsps_e2r} HSPs, resident path {hsps_res}"
+    assert step_crc["resident"] == step_crc["vector_abi"] == step_crc["e2e"], f"legs returned different HSP bytes: {step_crc}"
 
     total_bases = torch.tensor([float(query_bases)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -422,6 +442,9 @@ def run_ours(args):
             "setup_ms": {"ref_upload_encode": round((t1 - t0) * 1e3, 1), "seed_pos_table_build": round((t2 - t1) * 1e3, 1),
                          "query_upload_encode": round((t3 - t2) * 1e3, 1)},
             "wall_ms_per_step": round(wall_res / args.steps, 3),
+            "hsp_bytes_checksum": {"value": "%016x" % step_crc["resident"],
+                                   "note": "sum over units of crc32(HSP records) * (2u+1); identical for the resident, "
+                                           "e2e and vector-ABI legs (asserted)"},
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
