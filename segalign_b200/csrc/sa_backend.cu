@@ -173,22 +173,26 @@ void add_launches(uint64_t n) {
 }
 
 // ------------------------------------------------------------------ sequence planes
-int free_planes(SeqPlanes &p) {
-    if (p.b8) CU(cudaFree(p.b8), SA_ERR_FREE);
-    if (p.p2) CU(cudaFree(p.p2), SA_ERR_FREE);
-    if (p.m1) CU(cudaFree(p.m1), SA_ERR_FREE);
-    if (p.rec_base) CU(cudaFree(p.rec_base), SA_ERR_FREE);
+// Sequence planes come from the device's stream-ordered memory pool (release threshold = keep
+// everything): ClearQuery + SendQueryWriteRequest of the next block then reuse the previous block's
+// memory without a cudaFree / cudaMalloc pair -- those synchronise the device and, with several
+// processes on one box, cost tens of milliseconds per block.
+int free_planes(SeqPlanes &p, cudaStream_t st) {
+    if (p.b8) CU(cudaFreeAsync(p.b8, st), SA_ERR_FREE);
+    if (p.p2) CU(cudaFreeAsync(p.p2, st), SA_ERR_FREE);
+    if (p.m1) CU(cudaFreeAsync(p.m1, st), SA_ERR_FREE);
+    if (p.rec_base) CU(cudaFreeAsync(p.rec_base, st), SA_ERR_FREE);
     p = SeqPlanes();
     return SA_OK;
 }
 
-int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag) {
+int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag, cudaStream_t st) {
     p.len = len;
     p.words = ((size_t)len + 31) / 32 + PAD_WORDS;
-    cudaError_t e = cudaMalloc((void **)&p.b8, (size_t)len + 64);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p.p2, p.words * sizeof(uint64_t));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p.m1, p.words * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc((void **)&p.rec_base, (p.words + REC_FRONT + 1) * sizeof(uint4));
+    cudaError_t e = cudaMallocAsync((void **)&p.b8, (size_t)len + 64, st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.p2, p.words * sizeof(uint64_t), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.m1, p.words * sizeof(uint32_t), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.rec_base, (p.words + REC_FRONT + 1) * sizeof(uint4), st);
     p.rec = p.rec_base ? p.rec_base + REC_FRONT : nullptr;
     if (e != cudaSuccess)
         return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for %s failed with error \" %s \"",
@@ -207,18 +211,18 @@ void build_records(GpuCtx &g, SeqPlanes &p) {
 int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, SeqPlanes *rc,
                       const char *tag) {
     uint8_t *d_tmp = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d_tmp, (size_t)len + 64);
+    cudaError_t e = cudaMallocAsync((void **)&d_tmp, (size_t)len + 64, g.ctrl);
     if (e != cudaSuccess)
         return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for tmp_%s failed with error \" %s \"",
                     (unsigned long)len, tag, cudaGetErrorString(e));
     e = cudaMemcpyAsync(d_tmp, src, len, cudaMemcpyHostToDevice, g.ctrl);
     if (e != cudaSuccess) {
-        cudaFree(d_tmp);
+        cudaFreeAsync(d_tmp, g.ctrl);
         return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for %s failed with error \" %s \"",
                     (unsigned long)len, tag, cudaGetErrorString(e));
     }
-    TRY(alloc_planes(fwd, len, tag));
-    if (rc) TRY(alloc_planes(*rc, len, tag));
+    TRY(alloc_planes(fwd, len, tag, g.ctrl));
+    if (rc) TRY(alloc_planes(*rc, len, tag, g.ctrl));
     if (len > 0) {
         int grid = grid_for(((size_t)len + 15) / 16, 256);
         k_encode_b8<<<grid, 256, 0, g.ctrl>>>(d_tmp, len, fwd.b8, rc ? rc->b8 : nullptr);
@@ -232,8 +236,8 @@ int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, 
     if (rc) build_records(g, *rc);
     add_launches(rc ? 5 : 3);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
+    CU(cudaFreeAsync(d_tmp, g.ctrl), SA_ERR_FREE);
     CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
-    CU(cudaFree(d_tmp), SA_ERR_FREE);
     return SA_OK;
 }
 
@@ -621,6 +625,12 @@ int sa_initialize_interface_at(int first_device, int num_gpu) {
         G.gpus[i].device = first_device + i;
         CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
         CU(cudaStreamCreateWithFlags(&G.gpus[i].ctrl, cudaStreamNonBlocking), SA_ERR_KERNEL);
+        {   // keep freed block memory in the pool (see alloc_planes)
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ull;
+            CU(cudaDeviceGetDefaultMemPool(&pool, G.gpus[i].device), SA_ERR_MALLOC);
+            CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), SA_ERR_MALLOC);
+        }
     }
     fprintf(stderr, "Using %d GPU(s)\n", use);
     G.interface_ready = true;
@@ -860,7 +870,7 @@ int sa_generate_seed_pos_table(const char *ref_str, size_t start_addr, uint32_t 
 int sa_clear_ref(void) {
     for (auto &g : G.gpus) {
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
-        TRY(free_planes(g.ref));
+        TRY(free_planes(g.ref, g.ctrl));
         if (g.d_index) CU(cudaFree(g.d_index), SA_ERR_FREE);
         if (g.d_pos) CU(cudaFree(g.d_pos), SA_ERR_FREE);
         g.d_index = g.d_pos = nullptr;
@@ -897,8 +907,8 @@ int sa_clear_query(uint32_t buffer) {
     if (buffer >= SA_BUFFER_DEPTH) return fail(SA_ERR_ARG, "buffer %u out of range", buffer);
     for (auto &g : G.gpus) {
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
-        TRY(free_planes(g.q_fwd[buffer]));
-        TRY(free_planes(g.q_rc[buffer]));
+        TRY(free_planes(g.q_fwd[buffer], g.ctrl));
+        TRY(free_planes(g.q_rc[buffer], g.ctrl));
     }
     G.query_loaded[buffer] = false;
     return SA_OK;
@@ -1012,8 +1022,10 @@ int sa_shutdown_processor(void) {
         cudaSetDevice(g.device);
         for (auto *w : g.ws) destroy_workspace(w);
         g.ws.clear();
-        free_planes(g.ref);
-        for (int b = 0; b < SA_BUFFER_DEPTH; b++) { free_planes(g.q_fwd[b]); free_planes(g.q_rc[b]); }
+        free_planes(g.ref, g.ctrl);
+        for (int b = 0; b < SA_BUFFER_DEPTH; b++) { free_planes(g.q_fwd[b], g.ctrl); free_planes(g.q_rc[b], g.ctrl); }
+        if (g.ctrl) cudaStreamSynchronize(g.ctrl);
+        { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, g.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
         cudaFree(g.d_index); cudaFree(g.d_pos); cudaFree(g.d_sub_mat);
         g.d_index = g.d_pos = nullptr; g.d_sub_mat = nullptr;
         if (g.ctrl) cudaStreamDestroy(g.ctrl);
