@@ -42,11 +42,31 @@ def gen_worm_piece(rng):
     return ref, q
 
 
-H.GENERATORS.update(ecoli_self=gen_ecoli_self, ecoli_mut40=gen_ecoli_mut40, worm_piece=gen_worm_piece)
+def gen_chr1_like(rng):
+    """BASELINE configs[3] at reduced size: half soft-masked reference with long N runs, a 30 %-diverged
+    query with shared short N / IUPAC runs (they sit inside HSPs under --ambiguous=iupac) and its own
+    soft-masking; run with --notransition --ambiguous=iupac on the plus strand (IUPAC letters in the
+    query: the reference's host RevComp drops them, see harness.gen_shared_ambiguous)."""
+    n = 6_000_000
+    ref = genome.random_genome(n, rng)
+    q = genome.mutate(ref, 0.30, rng)
+    for s in rng.integers(0, n - 8, size=3000):
+        ref[s:s + 6] = ord("N"); q[s:s + 6] = ord("N")
+    for s in rng.integers(0, n - 8, size=3000):
+        ref[s:s + 2] = ord("R"); q[s:s + 2] = ord("R")
+    ref = genome.insert_runs(genome.soft_mask(ref, 0.5, rng), b"N", 3, 150_000, rng)
+    q = genome.soft_mask(q, 0.45, rng)
+    return ref, q[:4_000_000]
+
+
+H.GENERATORS.update(ecoli_self=gen_ecoli_self, ecoli_mut40=gen_ecoli_mut40, worm_piece=gen_worm_piece,
+                    chr1_like=gen_chr1_like)
 CASES = [
     H.Case("ecoli_mut40", "ecoli_mut40"),                      # BASELINE configs[0], throughput variant
     H.Case("worm_piece_20Mb_x_3Mb", "worm_piece"),             # configs[1] at reduced size, soft-masked
     H.Case("ecoli_self", "ecoli_self"),                        # configs[0]: main-diagonal blow-up (SURVEY 7)
+    H.Case("chr1_like_6Mb_x_4Mb_iupac_notransition", "chr1_like", transition=False, ambiguous="iupac",
+           strand="plus"),                                    # configs[3] flags at reduced size
 ]
 
 
