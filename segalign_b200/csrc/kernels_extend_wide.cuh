@@ -16,7 +16,7 @@
 //     otherwise it leaves with  s + sum,  max(M, s + maxpre)   (position updated on strict >).
 // So a warp takes 32 consecutive tiles of a direction at once: every lane summarises its tile,
 // two warp scans give every tile its entry state, the first tile that stops the walk (or needs
-// the cell-by-cell code: a non-ACGT cell, a block end) is finished by its own lane with the exact
+// the cell-by-cell code: a block end) is finished by its own lane with the exact
 // sequential tile code, and the walk either ends there or continues behind it.  `drop` is
 // over-estimated per 4-cell group (never under-estimated): a false alarm only costs a sequential
 // tile, never a different result.  The first-maximum tie rule (strict >) is kept by taking the
@@ -140,11 +140,28 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
         uint32_t m = 0xFFFFFFFFu;
         if (inside) m = load_m1_window(P.rm1, rc0) | load_m1_window(P.qm1, qc0);
         const bool clean = m == 0;
+        const bool summarised = inside; // tiles that touch a block end go to the cell-by-cell code (:420 rule)
         int sum = 0, maxpre = -(1 << 29), argpos = 0, minpre = 0, dropub = 0;
         if (clean) {
             uint64_t rw = load_p2_window(P.rp2, rc0), qw = load_p2_window(P.qp2, qc0);
             if (left) { rw = reverse_fields32(rw); qw = reverse_fields32(qw); }
             wide_tile_summary(lut_lane, rw, qw, sum, maxpre, argpos, minpre, dropub);
+        } else if (inside) {
+            // non-ACGT cells (N / IUPAC runs that score 0 under --ambiguous, soft cells, terminators):
+            // the same summary from the 1 B/base codes, exact drop.  A run of thousands of N is then
+            // 32 tiles per step like any other stretch; a terminator shows up as a drop > xdrop.
+            const int base = left ? (int)tt + 1 : (int)tt;
+            int s = 0, L = -(1 << 29), mn = 1 << 29, dub = 0, ap = 0;
+#pragma unroll 4
+            for (int j = 0; j < 32; j++) {
+                const uint32_t k = (uint32_t)(base + j);
+                const uint32_t rp = left ? r0 - k : r0 + k, qp = left ? q0 - k : q0 + k;
+                s += sub[__ldg(P.rb8 + rp) * 8 + __ldg(P.qb8 + qp)];
+                if (s > L) { L = s; ap = j; }
+                mn = min(mn, s);
+                dub = max(dub, L - s);
+            }
+            sum = s; maxpre = L; argpos = ap; minpre = mn; dropub = dub;
         }
         // ---- entry state of every tile: exclusive scans over the lanes in front of it
         int s_in = sum;
@@ -164,7 +181,7 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
         const int m_out = max(m_in, W.M);     // inclusive
         m_in = __shfl_up_sync(0xFFFFFFFFu, m_out, 1);
         if (lane == 0) m_in = W.M;            // running maximum in front of this tile
-        const bool flag = !clean || max(m_in - s_in - minpre, dropub) > X;
+        const bool flag = !summarised || max(m_in - s_in - minpre, dropub) > X;
         const unsigned fm = __ballot_sync(0xFFFFFFFFu, flag);
         const uint32_t T = fm ? (uint32_t)__ffs((int)fm) - 1u : 32u; // first tile that needs the cell-by-cell code
         // ---- state in front of tile T (behind tile 31 if no tile is flagged)
