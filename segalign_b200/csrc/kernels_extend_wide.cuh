@@ -140,16 +140,19 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
         uint32_t m = 0xFFFFFFFFu;
         if (inside) m = load_m1_window(P.rm1, rc0) | load_m1_window(P.qm1, qc0);
         const bool clean = m == 0;
-        const bool summarised = inside; // tiles that touch a block end go to the cell-by-cell code (:420 rule)
+        // tiles that touch a block end always go to the cell-by-cell code (:420 rule); tiles with non-ACGT
+        // cells do so unless such cells can be walked through (N / lower case not being terminators)
+        const bool summarised = clean || (inside && P.soft_runs);
         int sum = 0, maxpre = -(1 << 29), argpos = 0, minpre = 0, dropub = 0;
         if (clean) {
             uint64_t rw = load_p2_window(P.rp2, rc0), qw = load_p2_window(P.qp2, qc0);
             if (left) { rw = reverse_fields32(rw); qw = reverse_fields32(qw); }
             wide_tile_summary(lut_lane, rw, qw, sum, maxpre, argpos, minpre, dropub);
-        } else if (inside) {
-            // non-ACGT cells (N / IUPAC runs that score 0 under --ambiguous, soft cells, terminators):
-            // the same summary from the 1 B/base codes, exact drop.  A run of thousands of N is then
-            // 32 tiles per step like any other stretch; a terminator shows up as a drop > xdrop.
+        } else if (summarised) {
+            // non-ACGT cells under a matrix that lets a walk pass through them (N / IUPAC runs score 0
+            // with --ambiguous=n|iupac): the same summary from the 1 B/base codes, exact drop.  A run of
+            // thousands of N is then 32 tiles per step like any other stretch; a terminator cell shows
+            // up as a drop > xdrop (the rest of such a tile is irrelevant: it is walked cell by cell).
             const int base = left ? (int)tt + 1 : (int)tt;
             int s = 0, L = -(1 << 29), mn = 1 << 29, dub = 0, ap = 0;
 #pragma unroll 4
@@ -160,6 +163,7 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
                 if (s > L) { L = s; ap = j; }
                 mn = min(mn, s);
                 dub = max(dub, L - s);
+                if (dub > X) break;
             }
             sum = s; maxpre = L; argpos = ap; minpre = mn; dropub = dub;
         }

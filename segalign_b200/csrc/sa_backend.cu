@@ -388,6 +388,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
     P.diag_all_positive = G.diag_all_positive;
     P.scores_fit_int8 = G.filter_ok;
+    P.soft_runs = (((G.term_codes >> L_NT) & 1u) == 0 || ((G.term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
     F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
