@@ -35,9 +35,6 @@ namespace sa {
 #ifndef SA_SCR_Q_CAP
 #define SA_SCR_Q_CAP 64
 #endif
-#ifndef SA_SCR_REQ_LANES
-#define SA_SCR_REQ_LANES 6 // lanes that fetch the six records of one hit (6 or 2)
-#endif
 #ifndef SA_SCR_L2_HINTS
 #define SA_SCR_L2_HINTS 1 // reference records evict_last, seed positions evict_first (keeps the records L2-resident)
 #endif
@@ -166,6 +163,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     if (lane == 0) next_c = atomicAdd(counters + CTR_CHUNK, 1u);
     uint32_t row_tail = 0;         // rows handed out so far (monotonic; row id = counter mod 256)
     uint32_t pre_n = 0;            // hits whose records are already requested (the next round)
+    uint32_t r_next = 0;           // lane: reference anchor of its hit of that round
     bool exhausted = false;
     uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0;
     bool any_hits = false;
@@ -177,38 +175,16 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
         const uint32_t qpos = SRC == SRC_RANGE ? H.j0 + key / H.per : (uint32_t)__ldg(H.seeds + key);
         return qpos + H.seed_size;
     };
-    // reference records w-3 .. w+2 of n staged hits starting at ring position `from`: six
-    // neighbouring lanes per hit, 16 bytes each, straight into the staging buffer
-    auto request_records = [&](uint32_t from, uint32_t n) {
-#if SA_SCR_REQ_LANES == 2 || SA_SCR_REQ_LANES == 1
-        // L lanes per hit, 6/L consecutive records each: more L1 tag lookups than the six-lane mapping
-        // below (a 32-lane request touches more lines), a fraction of its address arithmetic
-        constexpr uint32_t L = SA_SCR_REQ_LANES, PER = SCREEN_RECS / L, HITS = 32u / L;
-        const uint32_t part = (lane % L) * PER;
-#pragma unroll
-        for (uint32_t pass = 0; pass < L; pass++) {
-            const uint32_t hs = pass * HITS + lane / L;
-            if (hs < n) {
-                const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)] + H.seed_size;
-                const uint4 *src = rrec_m3 + ((r >> 5) + part);
-                uint4 *dst = stage + hs * SCR_STAGE_STRIDE + part;
-#pragma unroll
-                for (uint32_t j = 0; j < PER; j++) {
-#if SA_SCR_L2_HINTS
-                    cp_async16_hint(dst + j, src + j, pol_keep);
-#else
-                    cp_async16(dst + j, src + j);
-#endif
-                }
-            }
-        }
-#else
+    // Reference records w-3 .. w+2 of the next round's n hits: six neighbouring lanes per hit, 16
+    // bytes each, straight into the staging buffer.  r_own = this lane's own hit of that round
+    // (anchor in the reference block); the loader lanes get the anchors by shuffle.
+    auto request_records = [&](uint32_t r_own, uint32_t n) {
 #pragma unroll
         for (uint32_t i = 0; i < SCREEN_RECS; i++) {
             const uint32_t f = i * 32u + lane;
             const uint32_t hs = f / SCREEN_RECS, rc = f - hs * SCREEN_RECS;
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, r_own, hs & 31u);
             if (hs < n) {
-                const uint32_t r = ring_r[(from + hs) & (SCR_RING - 1)] + H.seed_size;
 #if SA_SCR_L2_HINTS
                 cp_async16_hint(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc), pol_keep);
 #else
@@ -216,7 +192,6 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
 #endif
             }
         }
-#endif
     };
 
     for (;;) {
@@ -376,7 +351,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 __syncwarp();
                 n1 = min(tail - head, 32u);
                 safe_tail = tail;
-                request_records(head, n1);
+                r_next = lane < n1 ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
+                request_records(r_next, n1);
                 cp_async_commit();
                 cp_async_wait_all();
             } else {
@@ -394,7 +370,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             const uint32_t qr[SCREEN_ROW_WORDS] = {q_a.x, q_a.y, q_a.z, q_a.w, q_b.x, q_b.y, q_b.z, q_b.w, q_c.x, q_c.y, q_c.z, 0u};
             const uint32_t key = q_c.w + vkey; // seed order index of the hit's seed word
             __syncwarp();
-            if (have) r0 = ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size;
+            r0 = r_next; // this lane's anchor: read when the records were requested
             uint32_t rr[SCREEN_ROW_WORDS];
             {
                 const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
@@ -405,7 +381,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             __syncwarp(); // every lane holds its window: the staging buffer is free again
             head += n1;
             pre_n = min(safe_tail - head, 32u); // only positions that are known to have landed
-            if (pre_n) request_records(head, pre_n);
+            r_next = lane < pre_n ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
+            if (pre_n) request_records(r_next, pre_n);
             cp_async_commit(); // group "R": the records of the next round
             int bound; bool decided;
             const bool push = have && !screen_reject(rr, qr, C, bound, decided);
