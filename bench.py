@@ -439,6 +439,9 @@ def run_ours(args):
                                   "hsps": hsps_res // args.steps,
                                   "tile_walked_after_screen": st_res["walked"] // args.steps,
                                   "ext_cells_beyond_first_tile": int(ext_per_hit * st_res["hits"]) // args.steps},
+            "rates": {"seed_words_per_s": round(st_res["seeds"] / (ms_res * 1e-3), 1),
+                      "hits_per_s": round(st_res["hits"] / (ms_res * 1e-3), 1),
+                      "note": "rank 0, resident leg (SURVEY 8d asks for seeds/s and hits/s beside the headline)"},
             "setup_ms": {"ref_upload_encode": round((t1 - t0) * 1e3, 1), "seed_pos_table_build": round((t2 - t1) * 1e3, 1),
                          "query_upload_encode": round((t3 - t2) * 1e3, 1)},
             "wall_ms_per_step": round(wall_res / args.steps, 3),

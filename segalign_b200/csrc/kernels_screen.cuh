@@ -22,7 +22,7 @@
 
 namespace sa {
 
-// tuning knobs (overridable at build time: scripts/tune_filter3.sh measures the variants on the GPU)
+// tuning knobs (overridable at build time: scripts/experiments/tune_filter3.sh measures the variants on the GPU)
 #ifndef SA_SCR_THREADS
 #define SA_SCR_THREADS 256
 #endif
