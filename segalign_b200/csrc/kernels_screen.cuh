@@ -7,15 +7,16 @@
 // at 70 % and ~1400 instructions per hit: every lane gathered its own 16-byte records (one L1 tag
 // lookup per lane and record, ~7 per hit) and walked ~3 tiles through the pair LUT.  Here
 //
-//   1. query windows are aligned once per seed word (not per hit) and kept in shared memory:
-//      all hits of a seed word share the query anchor;
+//   1. query windows are aligned once per seed word (seed vectors) or once per query position
+//      (device seeding: the 13 words of a position share it), not per hit, and kept in shared
+//      memory: all hits of a seed word share the query anchor;
 //   2. the reference window of a hit (6 consecutive records = 96 bytes) is fetched by six
 //      neighbouring lanes with cp.async straight into shared memory: a 32-lane request touches
 //      ~9 lines instead of 32, the owner lane then reads its records with conflict-free LDS.128;
 //   3. the hit is decided by the popcount screen of screen_bound.h (~15 instructions per 16-cell
 //      block, 10 blocks) -- about 98 % of random hits end here;
 //   4. undecided hits are queued per warp and walked by the persistent-lane tile loop of
-//      kernels_filter.cuh (same code, same bound as before), 64 at a time.
+//      kernels_filter.cuh (same code, same bound as before), 32 to 63 at a time.
 #pragma once
 #include "kernels_filter.cuh"
 #include "screen_bound.h"
@@ -103,10 +104,11 @@ __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
 }
 
 // Work flow of one warp (all state below is warp-uniform unless it says "lane"):
-//   refill   while fewer than SCR_REFILL hits are staged: take the next group of 32 seed words
-//            (global counter, fetched one refill ahead), look their buckets up, align the query
-//            window of every seed word that has hits into a row of the row ring, expand the
-//            buckets into the hit ring (reference position + row id per hit; the positions are
+//   refill   while fewer than SCR_REFILL hits are staged: take the next group (global counter,
+//            fetched one refill ahead) -- 32 seed words of a seed vector, or 32 query positions
+//            with device seeding, expanded one variant at a time -- look the buckets up, align the
+//            query windows into rows of the row ring, expand the buckets into the hit ring
+//            (reference position + row id [+ variant] per hit; the positions are
 //            copied from the seed position table with cp.async and are first read two rounds
 //            later).  Hits of different groups queue up behind each other, so every round below
 //            has 32 hits until the very end of the call.
