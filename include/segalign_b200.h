@@ -169,6 +169,9 @@ typedef struct sa_pipeline_report {
     double seconds;
 } sa_pipeline_report;
 int sa_pipeline_run(const sa_pipeline_config *cfg, sa_pipeline_report *report);
+/* The host-only part of sa_pipeline_run: inputs -> blocks -> intervals, block name files, and
+ * report->{ref_blocks, query_blocks, intervals}.  Touches no GPU. */
+int sa_pipeline_plan(const sa_pipeline_config *cfg, sa_pipeline_report *report);
 /* src/main.cpp:187-268: the substitution matrix of --ambiguous / --xdrop (no --scoring file) */
 int sa_build_matrix(const char *ambiguous, int xdrop, int *sub_mat);
 

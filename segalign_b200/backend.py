@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
     "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds", "sa_write_segments",
-    "sa_pipeline_run", "sa_build_matrix",
+    "sa_pipeline_run", "sa_pipeline_plan", "sa_build_matrix",
 ]
 
 
@@ -97,6 +97,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_set_filter_kernel.argtypes = [C.c_int]
     lib.sa_build_matrix.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_int)]
     lib.sa_pipeline_run.argtypes = [C.c_void_p, C.c_void_p]
+    lib.sa_pipeline_plan.argtypes = [C.c_void_p, C.c_void_p]
     lib.sa_set_seed_shape.argtypes = [C.c_char_p]
     lib.sa_send_ref.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     lib.sa_generate_seed_pos_table.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_int]
@@ -238,8 +239,9 @@ class Backend:
         self._check(self.lib.sa_build_matrix(ambiguous.encode(), int(xdrop), m.ctypes.data_as(C.POINTER(C.c_int))))
         return m
 
-    def pipeline_run(self, ref_fasta, query_fasta, out_dir, **kw) -> dict:
-        """sa_pipeline_run: the Boost-free whole-genome driver."""
+    def pipeline_run(self, ref_fasta, query_fasta, out_dir, plan_only: bool = False, **kw) -> dict:
+        """sa_pipeline_run: the Boost-free whole-genome driver; plan_only = its host-only
+        part (sa_pipeline_plan: blocks, intervals, name files; no GPU)."""
         cfg = SaPipelineConfig()
         cfg.ref_fasta, cfg.query_fasta, cfg.out_dir = str(ref_fasta).encode(), str(query_fasta).encode(), str(out_dir).encode()
         keep = []
@@ -253,7 +255,8 @@ class Backend:
             else:
                 setattr(cfg, k, int(v))
         rep = SaPipelineReport()
-        self._check(self.lib.sa_pipeline_run(C.byref(cfg), C.byref(rep)))
+        fn = self.lib.sa_pipeline_plan if plan_only else self.lib.sa_pipeline_run
+        self._check(fn(C.byref(cfg), C.byref(rep)))
         return rep.as_dict()
 
     def set_filter_kernel(self, k: int) -> int:

@@ -48,6 +48,42 @@ def test_matrix_builder_matches_oracle(built):
             assert np.array_equal(be.build_matrix(amb, xdrop), sao.build_matrix(amb, xdrop)), (amb, xdrop)
 
 
+@pytest.mark.parametrize("block_size,interval", [(35_000, 16_000), (10_000, 5_000), (1_000_000, 30_000), (25_999, 100_000)])
+def test_driver_plan_blocks_and_intervals_match_python_restatement(built, tmp_path, block_size, interval):
+    """sa_pipeline_plan (host only, no GPU): FASTA parsing (wrapped lines, descriptions after the name,
+    CRLF, blank lines), the block closure rule and the interval count against segalign_b200/genome.py
+    (src/main.cpp:336-415, :380-393)."""
+    from segalign_b200.backend import Backend
+    rng = np.random.default_rng(block_size)
+    ref_chroms = [genome.random_genome(n, rng) for n in (30_000, 9_000, 26_000, 41_000, 12_000, 7_000, 1)]
+    query_chroms = [genome.random_genome(n, rng) for n in (20_000, 31_000, 26_000, 21_000, 8_000)]
+    _fasta(tmp_path / "ref.fa", ref_chroms, "chrR")
+    with open(tmp_path / "query.fa", "wb") as f:  # CRLF + blank lines + tab-separated description
+        for i, c in enumerate(query_chroms):
+            f.write(b">chrQ%d\tdesc\r\n\r\n" % i)
+            for k in range(0, c.size, 61):
+                f.write(c[k:k + 61].tobytes() + b"\r\n")
+    out = tmp_path / "plan"
+    out.mkdir()
+    rep = Backend().pipeline_run(tmp_path / "ref.fa", tmp_path / "query.fa", out, plan_only=True,
+                                 seq_block_size=block_size, lastz_interval=interval)
+    r_blocks = genome.make_blocks(ref_chroms, block_size)
+    q_blocks = genome.make_blocks(query_chroms, block_size)
+    assert rep["ref_blocks"] == len(r_blocks) and rep["query_blocks"] == len(q_blocks)
+    assert rep["intervals"] == len(r_blocks) * sum(len(genome.interval_list(b.size, 19, interval)) for b in q_blocks)
+    k = 0
+    for b, blk in enumerate(r_blocks):
+        n = int((blk == ord("&")).sum()) + 1
+        assert (out / f"ref_block{b}.name").read_text().split() == [f"chrR{i}" for i in range(k, k + n)]
+        k += n
+    k = 0
+    for b, blk in enumerate(q_blocks):
+        n = int((blk == ord("&")).sum()) + 1
+        assert (out / f"query_block{b}.name").read_text().split() == [f"chrQ{i}" for i in range(k, k + n)]
+        k += n
+    assert not (out / "lastz_commands.txt").exists()
+
+
 @pytest.mark.gpu
 def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     from oracle import sa_oracle_py as sao
