@@ -84,6 +84,21 @@ def test_driver_plan_blocks_and_intervals_match_python_restatement(built, tmp_pa
     assert not (out / "lastz_commands.txt").exists()
 
 
+def test_driver_fails_loudly_without_a_gpu(built, tmp_path):
+    """No CPU fallback anywhere: on a machine without a CUDA device the driver stops at
+    InitializeInterface with the reference's "no GPU" error (exit code 1, seed_filter_interface.cu:54-57)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from segalign_b200.backend import Backend, BackendError
+    rng = np.random.default_rng(1)
+    _fasta(tmp_path / "ref.fa", [genome.random_genome(5000, rng)], "chrR")
+    _fasta(tmp_path / "query.fa", [genome.random_genome(4000, rng)], "chrQ")
+    with pytest.raises(BackendError) as ei:
+        Backend().pipeline_run(tmp_path / "ref.fa", tmp_path / "query.fa", tmp_path, xdrop=910, hspthresh=3000, transition=1)
+    assert ei.value.code == -1
+
+
 @pytest.mark.gpu
 def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     from oracle import sa_oracle_py as sao
