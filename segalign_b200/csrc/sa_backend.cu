@@ -1082,24 +1082,65 @@ int sa_set_profiling(int enabled) { G.profiling = enabled != 0; return SA_OK; }
 // GetKmerIndexAtPos (common/ntcoding.cpp:43-61) restated as a rolling validity window.
 // Pure host code (no CUDA): it exists so that callers that still hand over seed vectors
 // (the reference ABI) can build them at memory speed from many threads.
+static const struct NtLut { uint8_t v[256]; NtLut() { memset(v, 4, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } g_nt_lut;
+
+#if defined(__x86_64__)
+// BMI2 path: the span is kept as a rolling 2-bit window (newest base in the low bits, so that the
+// first care position ends up most significant) and the k-mer is one PEXT of it.
+__attribute__((target("bmi2"))) static size_t host_chunk_seeds_bmi2(const unsigned char *s, uint32_t j0, uint32_t j1,
+                                                                    const ShapeDesc &sh, int transition, uint64_t *out) {
+    const int span = sh.span, w = sh.weight;
+    uint64_t care = 0;
+    for (int i = 0; i < w; i++) care |= 3ull << (2 * (span - 1 - sh.pos[i]));
+    const uint64_t keep = span >= 32 ? ~0ull : ((1ull << (2 * span)) - 1ull);
+    uint64_t xm[32];
+    int nv = 0;
+    if (transition)
+        for (int t = 0; t < w; t++)
+            if (sh.trans[t]) xm[nv++] = ((uint64_t)2 << (2 * t)) << 32;
+    uint64_t win = 0;
+    int64_t last_bad = -1;
+    for (uint32_t i = j0; i + 1 < j0 + (uint32_t)span; i++) {
+        uint32_t c = g_nt_lut.v[s[i]];
+        if (c > 3) { last_bad = i; c = 0; }
+        win = ((win << 2) | c) & keep;
+    }
+    size_t n = 0;
+    for (uint32_t j = j0; j < j1; j++) {
+        const uint32_t tail = j + (uint32_t)span - 1;
+        uint32_t c = g_nt_lut.v[s[tail]];
+        if (c > 3) { last_bad = tail; c = 0; }
+        win = ((win << 2) | c) & keep;
+        if (last_bad >= (int64_t)j) continue;
+        const uint64_t base = (__builtin_ia32_pext_di(win, care) << 32) + j;
+        out[n++] = base;
+        for (int v = 0; v < nv; v++) out[n++] = base ^ xm[v];
+    }
+    return n;
+}
+#endif
+
 size_t sa_host_chunk_seeds(const char *seq, size_t block_start, uint32_t j0, uint32_t j1,
                            int transition, uint64_t *out) {
     if (!G.shape_set || !seq || !out || j1 <= j0) return 0;
     const ShapeDesc sh = G.shape;
     const int span = sh.span, w = sh.weight;
     const unsigned char *s = reinterpret_cast<const unsigned char *>(seq) + block_start;
-    static const struct Lut { uint8_t v[256]; Lut() { memset(v, 4, 256); v['A'] = 0; v['C'] = 1; v['G'] = 2; v['T'] = 3; } } lut;
+#if defined(__x86_64__)
+    static const bool has_bmi2 = __builtin_cpu_supports("bmi2");
+    if (has_bmi2 && span <= 32) return host_chunk_seeds_bmi2(s, j0, j1, sh, transition, out);
+#endif
     size_t n = 0;
     // last_bad = index of the most recent non-ACGT character seen in [j0, j+span)
     int64_t last_bad = -1;
     for (uint32_t i = j0; i + 1 < j0 + (uint32_t)span && i < j1 + (uint32_t)span - 1; i++)
-        if (lut.v[s[i]] > 3) last_bad = i;
+        if (g_nt_lut.v[s[i]] > 3) last_bad = i;
     for (uint32_t j = j0; j < j1; j++) {
         uint32_t tail = j + (uint32_t)span - 1;
-        if (lut.v[s[tail]] > 3) last_bad = tail;
+        if (g_nt_lut.v[s[tail]] > 3) last_bad = tail;
         if (last_bad >= (int64_t)j) continue;
         uint64_t kmer = 0;
-        for (int i = 0; i < w; i++) kmer = (kmer << 2) | lut.v[s[j + sh.pos[i]]];
+        for (int i = 0; i < w; i++) kmer = (kmer << 2) | g_nt_lut.v[s[j + sh.pos[i]]];
         out[n++] = (kmer << 32) + j;
         if (transition) {
             for (int t = 0; t < w; t++)

@@ -43,6 +43,28 @@ def test_host_seed_words_match_oracle(shape, transition):
     assert np.array_equal(a, b) and a.size > 0
 
 
+@pytest.mark.parametrize("shape,transition", [("12of19", True), ("12of19", False), ("14of22", True), ("1101011", True),
+                                              ("1" * 14 + "0" * 17 + "1", True)])
+def test_native_host_seeding_matches_oracle(built, shape, transition):
+    """sa_host_chunk_seeds (the C ABI's host seeding loop, BMI2 rolling-window path where the CPU has it)
+    against the oracle's restatement of src/seeder.cpp:57-74 + ntcoding.cpp:43-61: same words, same order,
+    for ranges that start inside masked stretches, cross N runs and a separator, and tiny ranges."""
+    from segalign_b200.backend import Backend
+    rng = np.random.default_rng(11)
+    seq = genome.soft_mask(genome.random_genome(30000, rng), 0.12, rng, mean_run=40)
+    seq = genome.insert_runs(seq, b"N", 4, 30, rng)
+    seq[12345] = ord("&")
+    seq[:3] = A(b"acg")
+    sh = sao.Shape(shape)
+    be = Backend()
+    assert be.GenerateShapePos(shape) == sh.weight
+    last = seq.size - sh.span
+    for j0, j1 in [(0, last), (1, 2), (5000, 5001), (777, 12400), (12300, 12400), (last - 1, last), (29000, last)]:
+        want = sh.chunk_seeds(seq, j0, j1, transition)
+        got = be.host_chunk_seeds(seq, j0, j1, transition)
+        assert np.array_equal(got, want), (shape, transition, j0, j1)
+
+
 def test_revcomp_matches_reference_alphabet():
     s = A(b"ACGTacgtNn&")
     assert bytes(genome.revcomp_ascii(s)) == b"&nNacgtACGT"
