@@ -69,8 +69,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
 int sa_set_max_hits(uint32_t max_hits);
 uint32_t sa_get_max_hits(void);
 /* Test/measurement knob: which filter kernel the fused path launches from the next call on.
- * 3 = popcount screen + tile walk (default), 2 = two-phase tile walk, 1 = single-phase tile walk.
- * All three return identical results; 0 restores the default.  Returns the previous value. */
+ * 3 = popcount screen + tile walk (default), 2 = tile walk only.  Both return identical results;
+ * any other value restores the default.  Returns the previous value. */
 int sa_set_filter_kernel(int kernel);
 
 /* GenerateShapePos -- common/ntcoding.cpp:21-37.  pattern uses 'T'/'1' for care positions

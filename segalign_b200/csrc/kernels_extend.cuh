@@ -242,6 +242,7 @@ __device__ __forceinline__ bool finish_hit(const ExtendParams &P, uint32_t r0, u
 __device__ __forceinline__ uint32_t iteration_of(const uint32_t *__restrict__ hit_bound,
                                                  uint32_t num_iter, uint32_t h) {
     // number of iteration ends <= h
+    if (num_iter == 0xFFFFFFFFu) return 0; // the plan overflowed its arrays: the host discards this attempt and replays
     uint32_t lo = 0, hi = num_iter;
     while (lo < hi) {
         uint32_t mid = (lo + hi) >> 1;

@@ -130,6 +130,8 @@ struct HitSource {
     const uint32_t *index_table;
     const uint32_t *pos_table;
     uint32_t seed_size;
+    uint32_t index_size;       // 4^weight: seed words with a larger k-mer field are treated as empty buckets
+    uint32_t query_len;        // seed words whose span runs past the query block likewise (caller-supplied vectors)
     // SRC_RANGE: seed words of src/seeder.cpp:57-74 generated on the fly
     uint32_t j0;               // first query position of the range
     uint32_t per;              // words per valid position: 1 + transition variants
@@ -141,268 +143,24 @@ struct SurvRec {
     uint32_t r0, q0, key;
 };
 
-template <int SRC>
-__global__ void __launch_bounds__(FILTER_THREADS, 6)
-k_filter_hits(FilterParams P, HitSource H, const int *__restrict__ sub_mat, SurvRec *__restrict__ surv,
-              uint32_t surv_cap, uint32_t *__restrict__ counters) {
-    extern __shared__ uint32_t lut[];
-    __shared__ int diag[4];
-    for (int i = threadIdx.x; i < FILTER_LUT_WORDS; i += blockDim.x) {
-        const int idx = i >> 4, rn = idx >> 4, qn = idx & 15;
-        const int s0 = sub_mat[(rn & 3) * 8 + (qn & 3)], s1 = sub_mat[(rn >> 2) * 8 + (qn >> 2)];
-        lut[i] = (uint32_t)(uint8_t)(int8_t)s0 | ((uint32_t)(uint8_t)(int8_t)s1 << 8);
-    }
-    if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
-    __syncthreads();
-
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    // shared-space address of this lane's LUT column and the loop constants, pinned in registers
-    // (otherwise ptxas re-materialises them through the uniform datapath inside every group)
-    const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + (lane & 15u) * 4u;
-    const uint32_t mul = P.k_mul, m4 = P.k_m4;
-    const int X = P.xdrop;
-
-    // Work distribution: a warp stages up to FILTER_CHUNK hits at a time in shared memory and its
-    // lanes pick hits from the staged chunk as they become free.  SRC_HITS: a chunk is a slice of
-    // the hit list (one coalesced load).  Fused sources: the warp grabs 32 consecutive seed words
-    // from a global counter, looks their buckets up and expands them, FILTER_CHUNK hits at a time.
-    __shared__ uint2 hitbuf[FILTER_THREADS / 32][FILTER_CHUNK];
-    __shared__ uint8_t ownbuf[FILTER_THREADS / 32][FILTER_CHUNK];
-    uint2 *mybuf = hitbuf[threadIdx.x >> 5];
-    uint8_t *myown = ownbuf[threadIdx.x >> 5];
-    const uint32_t total_items = SRC == SRC_HITS ? min(H.plan[1], H.hits_cap) : H.num_items;
-    uint32_t key_base = 0;            // warp-uniform: hit index of staged slot 0 / seed index of the group's lane 0
-    uint32_t cursor = 0, limit = 0;   // warp-uniform: staged slots [cursor, limit) are unassigned
-    uint32_t g_total = 0, g_done = 0; // warp-uniform (fused): hits of the current seed group, hits already staged
-    bool exhausted = false;           // warp-uniform: the global work counter ran past the end
-    uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0; // per-warp totals (fused), flushed once at the end
-    bool any_hits = false;
-    // current hit of this lane
-    bool active = false, left = false;
-    uint32_t key = 0, r0 = 0, q0 = 0, t = 0;
-    int s = 0, M = 0, right_score = 0;
-    uint32_t ext_tiles = 0; // tiles walked beyond the first one of a direction (32-bit: stays in a register)
-
-    for (;;) {
-        const unsigned need = __ballot_sync(0xFFFFFFFFu, !active);
-        if (need && !exhausted) {
-            while (cursor == limit && !exhausted) { // staged chunk used up: stage the next one
-                if (SRC == SRC_HITS) {
-                    uint32_t c = 0;
-                    if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
-                    c = __shfl_sync(0xFFFFFFFFu, c, 0);
-                    const unsigned long long start = (unsigned long long)c * FILTER_CHUNK;
-                    key_base = start < total_items ? (uint32_t)start : total_items;
-                    const uint32_t cnt = min(total_items - key_base, FILTER_CHUNK);
-                    exhausted = cnt == 0;
-                    __syncwarp();
-#pragma unroll
-                    for (uint32_t k = 0; k < FILTER_CHUNK / 32; k++)
-                        if (k * 32u + lane < cnt) mybuf[k * 32u + lane] = __ldg(H.hits + key_base + k * 32u + lane);
-                    __syncwarp();
-                    cursor = 0; limit = cnt;
-                } else {
-                    if (g_done == g_total) { // next group of 32 seed words
-                        uint32_t c = 0;
-                        if (lane == 0) c = atomicAdd(counters + CTR_CHUNK, 1u);
-                        c = __shfl_sync(0xFFFFFFFFu, c, 0);
-                        const unsigned long long start = (unsigned long long)c * 32u;
-                        if (start >= total_items) { exhausted = true; break; }
-                        key_base = (uint32_t)start;
-                        g_done = 0;
-                        g_total = 0xFFFFFFFFu; // computed below together with the lanes' buckets
-                    }
-                    // this lane's seed word and bucket (recomputed per staged chunk: cheaper than
-                    // keeping five more registers alive across the extension trips)
-                    const uint32_t k = key_base + lane;
-                    uint32_t b_start = 0, n = 0, qa = 0;
-                    bool valid = false;
-                    if (k < total_items) {
-                        uint32_t kmer = 0, qpos = 0;
-                        if (SRC == SRC_SEEDS) {
-                            const uint64_t word = __ldg(H.seeds + k);
-                            kmer = (uint32_t)(word >> 32); qpos = (uint32_t)word;
-                            valid = true;
-                        } else {
-                            const uint32_t pi = k / H.per, v = k - pi * H.per;
-                            qpos = H.j0 + pi;
-                            uint64_t W; uint32_t Tw, Sw;
-                            load_window(P.qrec, (int)qpos, W, Tw, Sw);
-                            const uint32_t span_mask = H.shape.span >= 32 ? 0xFFFFFFFFu : ((1u << H.shape.span) - 1u);
-                            valid = ((Tw | Sw) & span_mask) == 0; // all span cells upper-case ACGT (ntcoding.cpp:47-52)
-                            for (int i = 0; i < H.shape.weight; i++) kmer = (kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
-                            if (v > 0) kmer ^= 2u << (2 * H.shape.tvar[v - 1]); // seeder.cpp:64-71
-                        }
-                        if (valid) {
-                            const uint32_t b_end = __ldg(H.index_table + kmer);
-                            b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
-                            n = b_end - b_start;
-                            qa = qpos + H.seed_size;
-                        }
-                    }
-                    uint32_t incl = n;
-#pragma unroll
-                    for (int off = 1; off < 32; off <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-                        if (lane >= (uint32_t)off) incl += up;
-                    }
-                    const uint32_t excl = incl - n;
-                    if (g_total == 0xFFFFFFFFu) { // first visit of this group: account for it
-                        g_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                        acc_hits += g_total;
-                        acc_seeds += __popc(__ballot_sync(0xFFFFFFFFu, valid));
-                        const unsigned with_hits = __ballot_sync(0xFFFFFFFFu, n > 0);
-                        if (with_hits) { acc_last = key_base + (31u - __clz(with_hits)); any_hits = true; } // groups come in ascending order per warp
-                        if (g_total == 0) continue;
-                    }
-                    const uint32_t cnt = min(g_total - g_done, FILTER_CHUNK);
-                    __syncwarp();
-#pragma unroll
-                    for (uint32_t kk = 0; kk < FILTER_CHUNK / 32; kk++) {
-                        const uint32_t f = g_done + kk * 32u + lane; // flat index inside the group
-                        // owner = first lane whose inclusive prefix exceeds f
-                        uint32_t lo = 0, hi = 31;
-#pragma unroll
-                        for (int it = 0; it < 5; it++) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            const uint32_t vmid = __shfl_sync(0xFFFFFFFFu, incl, mid);
-                            if (vmid > f) hi = mid; else lo = mid + 1;
-                        }
-                        const uint32_t o_excl = __shfl_sync(0xFFFFFFFFu, excl, lo);
-                        const uint32_t o_start = __shfl_sync(0xFFFFFFFFu, b_start, lo);
-                        const uint32_t o_q = __shfl_sync(0xFFFFFFFFu, qa, lo);
-                        if (kk * 32u + lane < cnt) {
-                            const uint32_t r = __ldg(H.pos_table + o_start + (f - o_excl)) + H.seed_size;
-                            mybuf[kk * 32u + lane] = make_uint2(r, o_q);
-                            myown[kk * 32u + lane] = (uint8_t)lo;
-                        }
-                    }
-                    __syncwarp();
-                    g_done += cnt;
-                    cursor = 0; limit = cnt;
-                }
-            }
-            const uint32_t avail = limit - cursor;
-            const uint32_t rank = __popc(need & lt_mask);
-            if (!active && rank < avail) {
-                const uint32_t slot = cursor + rank;
-                const uint2 hit = mybuf[slot];
-                r0 = hit.x; q0 = hit.y;
-                key = key_base + (SRC == SRC_HITS ? slot : (uint32_t)myown[slot]);
-                active = true; left = false; t = 0; s = 0; M = 0;
-            }
-            const uint32_t nneed = __popc(need);
-            cursor += nneed < avail ? nneed : avail;
-        }
-        if (!__any_sync(0xFFFFFFFFu, active)) {
-            if (exhausted) break;
-            continue;
-        }
-        if (active) {
-            // window of this trip: right = cells r0+t .. r0+t+31 ; left = cells r0-t-32 .. r0-t-1
-            const int cr = left ? (int)r0 - (int)t - 32 : (int)r0 + (int)t;
-            const int cq = left ? (int)q0 - (int)t - 32 : (int)q0 + (int)t;
-            uint64_t R, Q;
-            uint32_t Tr, Tq, Sr, Sq;
-            load_window(P.rrec, cr, R, Tr, Sr);
-            load_window(P.qrec, cq, Q, Tq, Sq);
-            uint32_t T = Tr | Tq, S = Sr | Sq;
-            uint32_t rl = (uint32_t)R, rh = (uint32_t)(R >> 32), ql = (uint32_t)Q, qh = (uint32_t)(Q >> 32);
-            // dp4a prefix selectors in processing order
-            uint32_t m1 = 0x00000001u, m2 = 0x00000101u, m3 = 0x00010101u;
-            if (left) {
-                // processing order = descending cells: reverse the BYTES (groups) of the window;
-                // inside a group the descending order is taken by the selectors
-                const uint32_t a = __byte_perm(rh, 0, 0x0123), b = __byte_perm(rl, 0, 0x0123);
-                const uint32_t c = __byte_perm(qh, 0, 0x0123), d = __byte_perm(ql, 0, 0x0123);
-                rl = a; rh = b; ql = c; qh = d;
-                T = __brev(T); S = __brev(S);
-                m1 = 0x01000000u; m2 = 0x01010000u; m3 = 0x01010100u;
-            }
-            const int n_eff = __clz(__brev(T));          // cells before the first terminator (32 if none)
-            const uint32_t valid = n_eff >= 32 ? 0xFFFFFFFFu : ((1u << n_eff) - 1u);
-            const bool survive = (S & valid) != 0;        // soft cell in range: let the exact kernel decide
-            // ---- the tile body is straight-line code: first all table lookups of the tile (independent
-            // of the running score, so their latencies overlap), then the short dependent chain.
-            // Groups at or past the one holding the first terminator are neutralised (score 0).
-            const int ng = survive ? 0 : (n_eff + 3) >> 2; // groups to visit (the last may run past the terminator)
-            bool dropped = false;
-            if (n_eff == 32 && !survive && rl == ql && rh == qh && P.diag_all_positive) {
-                s += diag_sum32_f(R, diag);               // all-match tile: strictly increasing prefix
-                M = max(M, s);
-            } else {
-                uint32_t sc[8];
-#pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const uint32_t y = g < 4 ? __byte_perm(rl, ql, 0x0040 | (g & 3) << 8 | (4 + (g & 3)))
-                                             : __byte_perm(rh, qh, 0x0040 | (g & 3) << 8 | (4 + (g & 3)));
-                    const uint32_t v = group_scores(lut_lane, mul, y);
-                    sc[g] = g < ng ? v : 0u;
-                }
-#pragma unroll
-                for (int g = 0; g < 8; g++) {
-                    const int p1 = __dp4a((int)sc[g], (int)m1, s);
-                    const int p2 = __dp4a((int)sc[g], (int)m2, s);
-                    const int p3 = __dp4a((int)sc[g], (int)m3, s);
-                    const int p4 = __dp4a((int)sc[g], (int)m4, s);
-                    const int mn = min(__vimin3_s32(p1, p2, p3), p4);
-                    // a cell more than xdrop below a maximum reached BEFORE this group: the reference's
-                    // walk has stopped by here.  Later groups of the tile still raise M (over-estimate).
-                    dropped |= mn < M - X;
-                    M = __vimax3_s32(__vimax3_s32(p1, p2, p3), p4, M);
-                    s = p4;
-                }
-            }
-            const bool done = dropped || n_eff < 32;
-            ext_tiles += t >= 32u ? 1u : 0u;
-            bool emit = false;
-            // M only grows: once the bound reaches hspthresh the hit is a survivor whatever follows, so
-            // the (possibly very long) rest of a homologous run is left to the exact kernel alone
-            if (survive || (left ? right_score : 0) + M >= P.hspthresh) {
-                emit = true;
-                active = false;
-            } else if (done) {
-                if (!left) {
-                    right_score = M;
-                    left = true; t = 0; s = 0; M = 0;
-                } else {
-                    emit = right_score + M >= P.hspthresh;
-                    active = false;
-                }
-            } else {
-                t += 32u;
-            }
-            if (emit) {
-                const uint32_t slot = atomicAdd(counters + CTR_SURV, 1u);
-                if (slot < surv_cap) { SurvRec rec; rec.r0 = r0; rec.q0 = q0; rec.key = key; surv[slot] = rec; }
-            }
-        }
-    }
-    if (ext_tiles) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), 32ull * ext_tiles);
-    if (SRC != SRC_HITS && lane == 0) {
-        if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits); // uint32 wrap-around like the reference's scan
-        if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
-        if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Two-phase variant of the filter kernel (the default).
+// The tile-walk filter kernel (general path, and the fallback for matrices the popcount screen of
+// kernels_screen.cuh does not admit).
 //
-// Profiling the persistent-lane kernel above showed ~240 of its ~420 instructions per 32-cell trip
-// outside the eight 4-cell groups: per-trip window loads and assembly, the per-lane walk state
-// machine and its share of work staging -- paid 2.9 times per hit -- plus one exposed L2 latency
-// per trip.  Almost every hit needs exactly: right tile 0, left tile 0, and usually left tile 1.
+// Profiling a first, purely persistent-lane version (one lane = one hit, one 32-cell tile per loop
+// trip; retired) showed ~240 of its ~420 instructions per trip outside the eight 4-cell groups:
+// per-trip window loads and assembly, the per-lane walk state machine and its share of work staging
+// -- paid 2.9 times per hit -- plus one exposed L2 latency per trip.  Almost every hit needs
+// exactly: right tile 0, left tile 0, and usually left tile 1.
 //   phase 1  a warp takes 32 fresh hits, one per lane, loads the 4+4 records that cover
 //            [r0-64, r0+32) / [q0-64, q0+32) with eight independent 16-byte loads, and walks
 //            right 0, left 0, left 1 as straight-line code: no state machine, no per-tile loads,
 //            all lanes in the same tile.  ~70 % of the hits are decided here.
 //   phase 2  hits whose walk is still open (right beyond 32 cells, left beyond 64) go to a per-warp
 //            continuation queue in shared memory with their walk state; when the queue holds
-//            CQ_DRAIN entries (or no fresh hits are left) the warp drains it with the persistent-
-//            lane loop of the kernel above.
-// Decisions and bounds are exactly those of k_filter_hits (same tile walk, same survivor rule).
+//            CQ_DRAIN entries (or no fresh hits are left) the warp drains it with a persistent-
+//            lane loop: each lane owns one open walk and advances it by one tile per trip; a lane
+//            whose walk is finished takes the next queued one.
 constexpr int CQ_CAP = 64;   // continuation queue entries per warp (static + dynamic shared memory <= 48 KB)
 constexpr int CQ_DRAIN = 32; // drain when at least this many are queued
 
@@ -499,7 +257,9 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
     uint8_t *myown = ownbuf[threadIdx.x >> 5];
     uint4(*myq)[2] = contq[threadIdx.x >> 5];
     const uint32_t total_items = SRC == SRC_HITS ? min(H.plan[1], H.hits_cap) : H.num_items;
-    uint32_t key_base = 0, cursor = 0, limit = 0, g_total = 0, g_done = 0; // as in k_filter_hits
+    // warp-uniform staging state: key_base = hit index of staged slot 0 / seed index of the group's lane 0;
+    // staged slots [cursor, limit) are unassigned; (fused) hits of the current seed group / already staged
+    uint32_t key_base = 0, cursor = 0, limit = 0, g_total = 0, g_done = 0;
     bool exhausted = false;
     uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0;
     bool any_hits = false;
@@ -512,7 +272,9 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
     };
 
     for (;;) {
-        // ---------------- stage the next chunk of fresh hits (identical to k_filter_hits)
+        // ---------------- stage the next chunk of fresh hits: SRC_HITS = a slice of the hit list (one
+        // coalesced load); fused sources = the warp grabs 32 consecutive seed words from a global counter,
+        // looks their buckets up and expands them, FILTER_CHUNK hits at a time
         while (cursor == limit && !exhausted) {
             if (SRC == SRC_HITS) {
                 uint32_t c = 0;
@@ -544,10 +306,12 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
                 bool valid = false;
                 if (k < total_items) {
                     uint32_t kmer = 0, qpos = 0;
+                    bool in_range = true;
                     if (SRC == SRC_SEEDS) {
                         const uint64_t word = __ldg(H.seeds + k);
                         kmer = (uint32_t)(word >> 32); qpos = (uint32_t)word;
                         valid = true;
+                        in_range = kmer < H.index_size && (unsigned long long)qpos + H.seed_size <= H.query_len;
                     } else {
                         const uint32_t pi = k / H.per, v = k - pi * H.per;
                         qpos = H.j0 + pi;
@@ -558,7 +322,7 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
                         for (int i = 0; i < H.shape.weight; i++) kmer = (kmer << 2) | (uint32_t)((W >> (2 * H.shape.pos[i])) & 3u);
                         if (v > 0) kmer ^= 2u << (2 * H.shape.tvar[v - 1]);
                     }
-                    if (valid) {
+                    if (valid && in_range) {
                         const uint32_t b_end = __ldg(H.index_table + kmer);
                         b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
                         n = b_end - b_start;

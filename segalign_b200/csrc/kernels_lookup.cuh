@@ -12,14 +12,22 @@ namespace sa {
 // bucket size per seed word: n = T[k] - (k ? T[k-1] : 0)   (seed_filter.cu:172-180)
 // The seed count lives in device memory (*d_num_seeds): with device-side seeding the host only
 // knows an upper bound (max_items) when it enqueues the call.  Slots past the count get 0 hits.
+// A seed word whose k-mer field lies outside the table or whose span runs past the query block (only a
+// caller-supplied vector can hold one; the reference's seeder never emits it) has an empty bucket.
+struct SeedBounds {
+    uint32_t index_size, query_len, seed_size;
+    __device__ __forceinline__ bool ok(uint64_t word) const {
+        return (uint32_t)(word >> 32) < index_size && (unsigned long long)(uint32_t)word + seed_size <= query_len;
+    }
+};
 __global__ void __launch_bounds__(256)
 k_count_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint32_t *__restrict__ d_num_seeds,
-             const uint32_t *__restrict__ index_table, uint32_t *__restrict__ counts) {
+             const uint32_t *__restrict__ index_table, SeedBounds B, uint32_t *__restrict__ counts) {
     const uint32_t num_seeds = min(*d_num_seeds, max_items);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < max_items; s += stride) {
         uint32_t n = 0;
-        if (s < num_seeds) {
+        if (s < num_seeds && B.ok(seeds[s])) {
             uint32_t kmer = (uint32_t)(seeds[s] >> 32);
             n = __ldg(index_table + kmer);
             if (kmer > 0) n -= __ldg(index_table + kmer - 1);
@@ -93,7 +101,7 @@ __global__ void k_plan_iterations(const uint32_t *__restrict__ prefix, uint32_t 
 __global__ void __launch_bounds__(256)
 k_expand_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint32_t *__restrict__ d_num_seeds,
               const uint32_t *__restrict__ index_table, const uint32_t *__restrict__ pos_table,
-              const uint32_t *__restrict__ prefix, uint32_t seed_size, uint2 *__restrict__ hits,
+              const uint32_t *__restrict__ prefix, uint32_t seed_size, SeedBounds B, uint2 *__restrict__ hits,
               uint32_t hits_cap) {
     const uint32_t num_seeds = min(*d_num_seeds, max_items);
     const uint32_t lane = threadIdx.x & 31u;
@@ -106,9 +114,11 @@ k_expand_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint
         if (s < num_seeds) {
             uint64_t word = seeds[s];
             uint32_t kmer = (uint32_t)(word >> 32);
-            uint32_t end = __ldg(index_table + kmer);
-            start = kmer > 0 ? __ldg(index_table + kmer - 1) : 0u;
-            n = end - start;
+            if (B.ok(word)) {
+                uint32_t end = __ldg(index_table + kmer);
+                start = kmer > 0 ? __ldg(index_table + kmer - 1) : 0u;
+                n = end - start;
+            }
             q = (uint32_t)word + seed_size;
             incl_global = prefix[s];
         }

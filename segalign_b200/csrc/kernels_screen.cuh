@@ -261,9 +261,12 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     const uint64_t word = __ldg(H.seeds + k);
                     const uint32_t kmer = (uint32_t)(word >> 32);
                     valid = true;
-                    const uint32_t b_end = __ldg(H.index_table + kmer);
-                    b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
-                    n = b_end - b_start;
+                    // a caller-supplied word outside the table / the query block has an empty bucket
+                    if (kmer < H.index_size && (unsigned long long)(uint32_t)word + H.seed_size <= H.query_len) {
+                        const uint32_t b_end = __ldg(H.index_table + kmer);
+                        b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                        n = b_end - b_start;
+                    }
                     qa = (uint32_t)word + H.seed_size;
                 }
             } else if (lane_valid) {

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -63,10 +64,10 @@ int fail(int code, const char *fmt, ...) {
         if (_r != SA_OK) return _r; \
     } while (0)
 
-constexpr int kSmCount = 148;
+int g_sm_count = 148; // multiProcessorCount of device 0, read in sa_initialize_interface_at
 inline int grid_for(size_t n, int block, int per_sm = 8) {
     size_t want = (n + block - 1) / block;
-    size_t cap = (size_t)kSmCount * per_sm;
+    size_t cap = (size_t)g_sm_count * per_sm;
     return (int)std::max<size_t>(1, std::min(want, cap));
 }
 
@@ -124,6 +125,8 @@ struct GpuCtx {
     uint32_t *d_pos = nullptr;
     uint32_t index_size = 0, num_pos = 0;
     int *d_sub_mat = nullptr;
+    uint8_t *d_ascii = nullptr; size_t ascii_cap = 0; // ASCII staging buffer of block uploads
+    cudaEvent_t ev_up = nullptr;                      // upload / peer copy of the current block has landed
     std::vector<Workspace *> ws;
 };
 
@@ -139,10 +142,9 @@ struct Global {
     bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
     bool use_fused = true;     // SEGALIGN_B200_FUSED=0 always takes the general (materialised hit list) path
-    int filter_grid = 0;
-    int filter2_grid = 0;      // two-phase tile-walk kernel (k_filter_hits2)
+    int filter2_grid = 0;      // tile-walk kernel (k_filter_hits2)
     int filter3_grid = 0;      // popcount screen + tile walk (k_filter_hits3), the default on the fused path
-    int filter_kernel = 3;     // SEGALIGN_B200_FILTER_KERNEL=1|2 select the single-phase / two-phase tile-walk kernels
+    int filter_kernel = 3;     // SEGALIGN_B200_FILTER_KERNEL=2 selects the tile-walk-only kernel on the fused path
     ScreenConsts screen = {};  // class scores of the popcount screen (screen_bound.h)
     int extend_grid = 0;
     int wide_grid = 0;         // k_extend_wide (warp per hit), SEGALIGN_B200_WIDE=0 sends all survivors to k_extend_hits
@@ -162,7 +164,7 @@ struct Global {
     // stats
     std::mutex stats_mu;
     sa_stats stats = {};
-    bool profiling = true; // per-phase CUDA events: two async records per phase, read after the call's final sync
+    bool profiling = false; // sa_set_profiling: per-phase CUDA events (adds a stream sync per call); off by default
 };
 
 Global G;
@@ -207,25 +209,27 @@ void build_records(GpuCtx &g, SeqPlanes &p) {
     p.term_codes = G.term_codes;
 }
 
-// upload ASCII and encode; fwd always, rc if rc != nullptr
-int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, SeqPlanes *rc,
-                      const char *tag) {
-    uint8_t *d_tmp = nullptr;
-    cudaError_t e = cudaMallocAsync((void **)&d_tmp, (size_t)len + 64, g.ctrl);
+// ASCII staging buffer of one GPU (plain cudaMalloc, kept and grown: peer copies read it)
+int ensure_ascii(GpuCtx &g, size_t len) {
+    if (g.d_ascii && g.ascii_cap >= len + 64) return SA_OK;
+    if (g.d_ascii) CU(cudaFree(g.d_ascii), SA_ERR_FREE);
+    g.d_ascii = nullptr; g.ascii_cap = 0;
+    const size_t cap = len + len / 8 + 4096;
+    cudaError_t e = cudaMalloc((void **)&g.d_ascii, cap);
     if (e != cudaSuccess)
-        return fail(SA_ERR_MALLOC, "cudaMalloc of %lu bytes for tmp_%s failed with error \" %s \"",
-                    (unsigned long)len, tag, cudaGetErrorString(e));
-    e = cudaMemcpyAsync(d_tmp, src, len, cudaMemcpyHostToDevice, g.ctrl);
-    if (e != cudaSuccess) {
-        cudaFreeAsync(d_tmp, g.ctrl);
-        return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for %s failed with error \" %s \"",
-                    (unsigned long)len, tag, cudaGetErrorString(e));
-    }
+        return fail(SA_ERR_MALLOC, "cudaMalloc of %zu bytes for the ASCII staging buffer failed with error \" %s \"",
+                    cap, cudaGetErrorString(e));
+    g.ascii_cap = cap;
+    return SA_OK;
+}
+
+// encode the ASCII block in g.d_ascii into the planes (async on the control stream); fwd always, rc if rc != nullptr
+int enqueue_encode(GpuCtx &g, uint32_t len, SeqPlanes &fwd, SeqPlanes *rc, const char *tag) {
     TRY(alloc_planes(fwd, len, tag, g.ctrl));
     if (rc) TRY(alloc_planes(*rc, len, tag, g.ctrl));
     if (len > 0) {
         int grid = grid_for(((size_t)len + 15) / 16, 256);
-        k_encode_b8<<<grid, 256, 0, g.ctrl>>>(d_tmp, len, fwd.b8, rc ? rc->b8 : nullptr);
+        k_encode_b8<<<grid, 256, 0, g.ctrl>>>(g.d_ascii, len, fwd.b8, rc ? rc->b8 : nullptr);
     }
     k_pack_planes<<<grid_for(fwd.words, 256), 256, 0, g.ctrl>>>(fwd.b8, len, fwd.p2, fwd.m1,
                                                                  (uint32_t)fwd.words);
@@ -236,8 +240,47 @@ int upload_and_encode(GpuCtx &g, const char *src, uint32_t len, SeqPlanes &fwd, 
     if (rc) build_records(g, *rc);
     add_launches(rc ? 5 : 3);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
-    CU(cudaFreeAsync(d_tmp, g.ctrl), SA_ERR_FREE);
-    CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+    return SA_OK;
+}
+
+// One block (reference, or query slot `slot` when slot >= 0) onto EVERY GPU of the pool: the ASCII bytes
+// cross PCIe once (to GPU 0) and reach the other GPUs by peer copies over NVLink; each GPU then encodes
+// its own planes.  Everything is enqueued on the per-GPU control streams first and awaited at the end,
+// so the GPUs work concurrently (the reference uploads and encodes GPU after GPU with blocking copies,
+// common/seed_filter_interface.cu:82-101, src/seed_filter.cu:899-919).
+int upload_block_all_gpus(const char *src, uint32_t len, int slot, const char *tag) {
+    const size_t n = G.gpus.size();
+    GpuCtx &g0 = G.gpus[0];
+    CU(cudaSetDevice(g0.device), SA_ERR_SET_DEVICE);
+    TRY(ensure_ascii(g0, len));
+    if (len) {
+        cudaError_t e = cudaMemcpyAsync(g0.d_ascii, src, len, cudaMemcpyHostToDevice, g0.ctrl);
+        if (e != cudaSuccess)
+            return fail(SA_ERR_MEMCPY, "cudaMemcpy of %lu bytes for %s failed with error \" %s \"",
+                        (unsigned long)len, tag, cudaGetErrorString(e));
+    }
+    CU(cudaEventRecord(g0.ev_up, g0.ctrl), SA_ERR_KERNEL);
+    for (size_t i = 1; i < n; i++) {
+        GpuCtx &g = G.gpus[i];
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        TRY(ensure_ascii(g, len));
+        CU(cudaStreamWaitEvent(g.ctrl, g0.ev_up, 0), SA_ERR_KERNEL);
+        if (len) CU(cudaMemcpyPeerAsync(g.d_ascii, g.device, g0.d_ascii, g0.device, len, g.ctrl), SA_ERR_MEMCPY);
+        CU(cudaEventRecord(g.ev_up, g.ctrl), SA_ERR_KERNEL);
+    }
+    for (size_t i = 0; i < n; i++) {
+        GpuCtx &g = G.gpus[i];
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        if (slot < 0) TRY(enqueue_encode(g, len, g.ref, nullptr, tag));
+        else TRY(enqueue_encode(g, len, g.q_fwd[slot], &g.q_rc[slot], tag));
+    }
+    // GPU 0's staging buffer may be overwritten by the next upload only after every peer has read it
+    CU(cudaSetDevice(g0.device), SA_ERR_SET_DEVICE);
+    for (size_t i = 1; i < n; i++) CU(cudaStreamWaitEvent(g0.ctrl, G.gpus[i].ev_up, 0), SA_ERR_KERNEL);
+    for (size_t i = 0; i < n; i++) {
+        CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
+        CU(cudaStreamSynchronize(G.gpus[i].ctrl), SA_ERR_KERNEL);
+    }
     return SA_OK;
 }
 
@@ -397,6 +440,8 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     H.plan = w->d_plan;
     H.num_items = max_items;
     H.index_table = g.d_index; H.pos_table = g.d_pos; H.seed_size = G.seed_size;
+    H.index_size = g.index_size; H.query_len = q.len;
+    const SeedBounds SB = {g.index_size, q.len, G.seed_size};
     H.j0 = in.q_start; H.per = in.per; H.shape = G.shape;
     DedupTable D;
     D.k0 = w->d_dedup; D.k1 = w->d_dedup + kDedupSlots;
@@ -423,11 +468,6 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
                     k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 else
                     k_filter_hits3<SRC_RANGE><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
-            } else if (G.filter_kernel == 1) {
-                if (in.src == SRC_SEEDS)
-                    k_filter_hits<SRC_SEEDS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
-                else
-                    k_filter_hits<SRC_RANGE><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
             } else {
                 if (in.src == SRC_SEEDS)
                     k_filter_hits2<SRC_SEEDS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
@@ -449,7 +489,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
             TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
             // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
-            k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, w->d_prefix);
+            k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, SB, w->d_prefix);
             CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
             // 2. iteration plan on the device (seed_filter.cu:718-745)
             k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, max_items, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
@@ -457,16 +497,13 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             pt.mark(PH_PLAN);
             // 3. flat hit expansion (seed_filter.cu:760)
             k_expand_hits<<<grid_for(((size_t)max_items + 31) / 32 * 32, 256), 256, 0, st>>>(
-                w->d_seeds, max_items, w->d_plan + 2, g.d_index, g.d_pos, w->d_prefix, G.seed_size, w->d_hits, hits_cap);
+                w->d_seeds, max_items, w->d_plan + 2, g.d_index, g.d_pos, w->d_prefix, G.seed_size, SB, w->d_hits, hits_cap);
             pt.mark(PH_LOOKUP);
             launches += 5;
             // 4a. stage A: conservative score bound over all hits -> survivor records
             if (filter) {
                 H.hits = w->d_hits; H.hits_cap = hits_cap;
-                if (G.filter_kernel == 1)
-                    k_filter_hits<SRC_HITS><<<G.filter_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
-                else
-                    k_filter_hits2<SRC_HITS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                k_filter_hits2<SRC_HITS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 launches++;
                 pt.mark(PH_FILTER);
             }
@@ -577,6 +614,9 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     *out = res;
     *out_count = n_final + 1;
     if (out_num_seeds) *out_num_seeds = num_seeds;
+    float ph_ms[PH_COUNT] = {};
+    if (pt.on) // event queries stay outside the stats lock: concurrent callers must not serialise on them
+        for (int p = PH_SEEDS; p < PH_COUNT; p++) ph_ms[p] = pt.ms((Phase)p);
     {
         std::lock_guard<std::mutex> l(G.stats_mu);
         sa_stats &s = G.stats;
@@ -585,13 +625,13 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         s.launches += launches;
         s.walked += n_walked;
         if (pt.on) {
-            s.ms_h2d += pt.ms(PH_SEEDS);
-            s.ms_count_scan += pt.ms(PH_PLAN);
-            s.ms_lookup += pt.ms(PH_LOOKUP);
-            s.ms_prefilter += pt.ms(PH_FILTER);
-            s.ms_extend += pt.ms(PH_EXTEND);
-            s.ms_sort += pt.ms(PH_SORT);
-            s.ms_d2h += pt.ms(PH_D2H);
+            s.ms_h2d += ph_ms[PH_SEEDS];
+            s.ms_count_scan += ph_ms[PH_PLAN];
+            s.ms_lookup += ph_ms[PH_LOOKUP];
+            s.ms_prefilter += ph_ms[PH_FILTER];
+            s.ms_extend += ph_ms[PH_EXTEND];
+            s.ms_sort += ph_ms[PH_SORT];
+            s.ms_d2h += ph_ms[PH_D2H];
         }
     }
     return SA_OK;
@@ -626,6 +666,15 @@ int sa_initialize_interface_at(int first_device, int num_gpu) {
         G.gpus[i].device = first_device + i;
         CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
         CU(cudaStreamCreateWithFlags(&G.gpus[i].ctrl, cudaStreamNonBlocking), SA_ERR_KERNEL);
+        CU(cudaEventCreateWithFlags(&G.gpus[i].ev_up, cudaEventDisableTiming), SA_ERR_KERNEL);
+        if (i == 0) CU(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, G.gpus[i].device), SA_ERR_KERNEL);
+        if (i > 0) { // block uploads reach this GPU by a peer copy from the first one: direct over NVLink when possible
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, G.gpus[i].device, G.gpus[0].device) == cudaSuccess && can) {
+                cudaError_t pe = cudaDeviceEnablePeerAccess(G.gpus[0].device, 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError(); // already enabled / unsupported: cudaMemcpyPeerAsync stages instead
+            }
+        }
         {   // keep freed block memory in the pool (see alloc_planes)
             cudaMemPool_t pool;
             unsigned long long keep = ~0ull;
@@ -686,19 +735,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
         CU(cudaMalloc((void **)&g.d_sub_mat, 64 * sizeof(int)), SA_ERR_MALLOC);
         CU(cudaMemcpy(g.d_sub_mat, sub_mat, 64 * sizeof(int), cudaMemcpyHostToDevice), SA_ERR_MEMCPY);
-        int per_sm = 0, sms = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_filter_hits<SRC_RANGE>, FILTER_THREADS,
-                                                         FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
+        int sms = 0;
         CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device), SA_ERR_KERNEL);
-        // tuning knobs (experiments): resident filter CTAs per SM and the shared-memory carve-out
-        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm = std::min(per_sm, atoi(e));
-        if (const char *e = getenv("SEGALIGN_B200_FILTER_CARVEOUT")) {
-            int pct = atoi(e);
-            cudaFuncSetAttribute(k_filter_hits<SRC_RANGE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_filter_hits<SRC_SEEDS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_filter_hits<SRC_HITS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        }
-        G.filter_grid = std::max(1, per_sm) * std::max(1, sms);
         int per_sm2 = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_filter_hits2<SRC_RANGE>, FILTER_THREADS,
                                                          FILTER_LUT_WORDS * sizeof(uint32_t)), SA_ERR_KERNEL);
@@ -715,7 +753,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm3 = atoi(e);
         G.filter3_grid = std::max(1, per_sm3) * std::max(1, sms);
         G.filter_kernel = 3;
-        if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) { int v = atoi(e); if (v >= 1 && v <= 3) G.filter_kernel = v; }
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) { int v = atoi(e); if (v == 2 || v == 3) G.filter_kernel = v; }
         G.extend_grid = 8 * std::max(1, sms); // one-warp blocks, persistent over the work list
         if (const char *e = getenv("SEGALIGN_B200_EXTEND_CTAS")) if (atoi(e) > 0) G.extend_grid = atoi(e) * std::max(1, sms);
         G.wide_grid = 4 * std::max(1, sms);   // four-warp blocks, one warp per hit
@@ -752,7 +790,7 @@ int sa_set_max_hits(uint32_t max_hits) {
 uint32_t sa_get_max_hits(void) { return G.max_hits; }
 int sa_set_filter_kernel(int kernel) {
     const int prev = G.filter_kernel;
-    G.filter_kernel = (kernel >= 1 && kernel <= 3) ? kernel : 3;
+    G.filter_kernel = kernel == 2 ? 2 : 3;
     return prev;
 }
 
@@ -779,23 +817,33 @@ int sa_set_seed_shape(const char *pattern) {
 int sa_send_ref(const char *seq, size_t start_addr, uint32_t len) {
     if (!G.interface_ready) return fail(SA_ERR_STATE, "InitializeInterface has not been called");
     if (G.ref_loaded) return fail(SA_ERR_STATE, "ClearRef must precede a second SendRefWriteRequest");
+    if (!seq && len) return fail(SA_ERR_ARG, "seq is NULL");
     G.ref_len = len;
-    for (auto &g : G.gpus) {
-        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, g.ctrl);
-        TRY(upload_and_encode(g, seq + start_addr, len, g.ref, nullptr, "ref_seq"));
-        cudaEventRecord(e1, g.ctrl);
-        cudaEventSynchronize(e1);
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const auto t0 = std::chrono::steady_clock::now();
+    TRY(upload_block_all_gpus(seq + start_addr, len, -1, "ref_seq"));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
         std::lock_guard<std::mutex> l(G.stats_mu);
-        G.stats.ms_ref_encode += ms;
+        G.stats.ms_ref_encode += ms; // wall time of the whole pool (the GPUs work concurrently)
     }
     G.ref_loaded = true;
     return SA_OK;
 }
+
+namespace {
+// device buffers of one GPU's table build; whatever is still owned is freed on every exit path
+struct TableBuild {
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr, *index = nullptr;
+    void *temp = nullptr;
+    uint32_t *num_pos_host = nullptr; // pinned
+    int device = 0;
+    ~TableBuild() {
+        cudaSetDevice(device);
+        cudaFree(keys_a); cudaFree(keys_b); cudaFree(vals_a); cudaFree(vals_b); cudaFree(index); cudaFree(temp);
+        if (num_pos_host) cudaFreeHost(num_pos_host);
+    }
+};
+} // namespace
 
 int sa_generate_seed_pos_table(const char *ref_str, size_t start_addr, uint32_t ref_length,
                                uint32_t step, int shape_size, int kmer_size) {
@@ -812,56 +860,68 @@ int sa_generate_seed_pos_table(const char *ref_str, size_t start_addr, uint32_t 
     uint32_t num_steps = ref_length >= (uint32_t)shape_size ? (ref_length - shape_size + offset) / step : 0;
     uint32_t index_size = 1u << (2 * kmer_size);
     int end_bit = 2 * kmer_size + 1;
-    for (auto &g : G.gpus) {
+    const auto t0 = std::chrono::steady_clock::now();
+    const size_t n = std::max<uint32_t>(num_steps, 1);
+    const size_t ngpu = G.gpus.size();
+    // Every GPU builds its own copy from its resident encoded block (no table crosses PCIe or NVLink;
+    // the reference builds on the host and uploads ~4 bytes per base to every GPU in turn,
+    // common/seed_pos_table.cu:33-47).  Phase 1 enqueues the whole build on every control stream,
+    // phase 2 waits: the GPUs run concurrently.
+    std::vector<TableBuild> tb(ngpu);
+    std::vector<cub::DoubleBuffer<uint32_t>> dks(ngpu), dvs(ngpu);
+    uint64_t launches = 0;
+    for (size_t i = 0; i < ngpu; i++) {
+        GpuCtx &g = G.gpus[i];
+        TableBuild &t = tb[i];
+        t.device = g.device;
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
         cudaStream_t st = g.ctrl;
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, st);
-        uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr;
-        size_t n = std::max<uint32_t>(num_steps, 1);
-        CU(cudaMalloc((void **)&g.d_index, (size_t)index_size * sizeof(uint32_t)), SA_ERR_MALLOC);
-        CU(cudaMemsetAsync(g.d_index, 0, (size_t)index_size * sizeof(uint32_t), st), SA_ERR_MEMCPY);
-        CU(cudaMalloc((void **)&keys_a, n * 4), SA_ERR_MALLOC);
-        CU(cudaMalloc((void **)&keys_b, n * 4), SA_ERR_MALLOC);
-        CU(cudaMalloc((void **)&vals_a, n * 4), SA_ERR_MALLOC);
-        CU(cudaMalloc((void **)&vals_b, n * 4), SA_ERR_MALLOC);
-        uint64_t launches = 0;
+        CU(cudaMalloc((void **)&t.index, (size_t)index_size * sizeof(uint32_t)), SA_ERR_MALLOC);
+        CU(cudaMemsetAsync(t.index, 0, (size_t)index_size * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        CU(cudaMalloc((void **)&t.keys_a, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&t.keys_b, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&t.vals_a, n * 4), SA_ERR_MALLOC);
+        CU(cudaMalloc((void **)&t.vals_b, n * 4), SA_ERR_MALLOC);
+        CU(cudaMallocHost((void **)&t.num_pos_host, sizeof(uint32_t)), SA_ERR_MALLOC);
         if (num_steps > 0) {
             k_table_keys<<<grid_for(num_steps, 256), 256, 0, st>>>(g.ref.p2, g.ref.m1, G.shape, start_offset, step,
-                                                                   num_steps, keys_a, vals_a, g.d_index);
+                                                                   num_steps, t.keys_a, t.vals_a, t.index);
             launches++;
         }
         // histogram -> inclusive end offsets (seed_pos_table.cu:83; device sees index_table+1)
         size_t bytes = 0, bytes2 = 0;
-        CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, g.d_index, g.d_index, (int)index_size, st), SA_ERR_KERNEL);
-        cub::DoubleBuffer<uint32_t> dk(keys_a, keys_b), dv(vals_a, vals_b);
-        CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes2, dk, dv, (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
-        void *d_temp = nullptr;
-        CU(cudaMalloc(&d_temp, std::max(bytes, bytes2) + 256), SA_ERR_MALLOC);
-        CU(cub::DeviceScan::InclusiveSum(d_temp, bytes, g.d_index, g.d_index, (int)index_size, st), SA_ERR_KERNEL);
+        CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, t.index, t.index, (int)index_size, st), SA_ERR_KERNEL);
+        dks[i] = cub::DoubleBuffer<uint32_t>(t.keys_a, t.keys_b);
+        dvs[i] = cub::DoubleBuffer<uint32_t>(t.vals_a, t.vals_b);
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes2, dks[i], dvs[i], (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
+        CU(cudaMalloc(&t.temp, std::max(bytes, bytes2) + 256), SA_ERR_MALLOC);
+        CU(cub::DeviceScan::InclusiveSum(t.temp, bytes, t.index, t.index, (int)index_size, st), SA_ERR_KERNEL);
         launches += 2;
-        uint32_t num_pos = 0;
-        CU(cudaMemcpyAsync(&num_pos, g.d_index + index_size - 1, 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+        CU(cudaMemcpyAsync(t.num_pos_host, t.index + index_size - 1, 4, cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
         if (num_steps > 0) {
-            CU(cub::DeviceRadixSort::SortPairs(d_temp, bytes2, dk, dv, (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
+            CU(cub::DeviceRadixSort::SortPairs(t.temp, bytes2, dks[i], dvs[i], (int)num_steps, 0, end_bit, st), SA_ERR_KERNEL);
             launches += 2 * ((end_bit + 7) / 8) + 1;
         }
-        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-        CU(cudaMalloc((void **)&g.d_pos, std::max<size_t>(num_pos, 1) * sizeof(uint32_t)), SA_ERR_MALLOC);
-        if (num_pos > 0)
-            CU(cudaMemcpyAsync(g.d_pos, dv.Current(), (size_t)num_pos * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st), SA_ERR_MEMCPY);
-        cudaEventRecord(e1, st);
-        CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        CU(cudaFree(keys_a), SA_ERR_FREE); CU(cudaFree(keys_b), SA_ERR_FREE);
-        CU(cudaFree(vals_a), SA_ERR_FREE); CU(cudaFree(vals_b), SA_ERR_FREE);
-        CU(cudaFree(d_temp), SA_ERR_FREE);
+        CU(cudaGetLastError(), SA_ERR_KERNEL);
+    }
+    for (size_t i = 0; i < ngpu; i++) {
+        GpuCtx &g = G.gpus[i];
+        TableBuild &t = tb[i];
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+        // the sorted value buffer IS the position table (positions of invalid words sort behind num_pos)
+        uint32_t *pos = dvs[i].Current();
+        if (pos == t.vals_a) t.vals_a = nullptr; else t.vals_b = nullptr;
+        g.d_pos = pos;
+        g.d_index = t.index; t.index = nullptr;
         g.index_size = index_size;
-        g.num_pos = num_pos;
+        g.num_pos = *t.num_pos_host;
+    }
+    tb.clear(); // frees the key buffers, the spare value buffer and the temporaries
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
         std::lock_guard<std::mutex> l(G.stats_mu);
-        G.stats.ms_table_build += ms;
+        G.stats.ms_table_build += ms; // wall time of the whole pool
         G.stats.launches += launches;
     }
     G.table_ready = true;
@@ -885,20 +945,15 @@ int sa_send_query(const char *query_base, size_t start_addr, uint32_t len, uint3
     if (!G.interface_ready) return fail(SA_ERR_STATE, "InitializeInterface has not been called");
     if (buffer >= SA_BUFFER_DEPTH) return fail(SA_ERR_ARG, "buffer %u out of range", buffer);
     if (G.query_loaded[buffer]) return fail(SA_ERR_STATE, "ClearQuery(%u) must precede a refill", buffer);
+    if (!query_base && len) return fail(SA_ERR_ARG, "query_base is NULL");
     G.query_len[buffer] = len;
-    for (auto &g : G.gpus) {
-        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
-        cudaEventRecord(e0, g.ctrl);
-        TRY(upload_and_encode(g, query_base + start_addr, len, g.q_fwd[buffer], &g.q_rc[buffer], "query_seq"));
-        cudaEventRecord(e1, g.ctrl);
-        cudaEventSynchronize(e1);
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    const auto t0 = std::chrono::steady_clock::now();
+    TRY(upload_block_all_gpus(query_base + start_addr, len, (int)buffer, "query_seq"));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    {
         std::lock_guard<std::mutex> l(G.stats_mu);
         G.stats.ms_query_encode += ms;
-        G.stats.h2d_bytes += len;
+        G.stats.h2d_bytes += len; // the block crosses PCIe once; the other GPUs get it by peer copy
     }
     G.query_loaded[buffer] = true;
     return SA_OK;
@@ -1027,8 +1082,10 @@ int sa_shutdown_processor(void) {
         for (int b = 0; b < SA_BUFFER_DEPTH; b++) { free_planes(g.q_fwd[b], g.ctrl); free_planes(g.q_rc[b], g.ctrl); }
         if (g.ctrl) cudaStreamSynchronize(g.ctrl);
         { cudaMemPool_t pool; if (cudaDeviceGetDefaultMemPool(&pool, g.device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0); }
-        cudaFree(g.d_index); cudaFree(g.d_pos); cudaFree(g.d_sub_mat);
-        g.d_index = g.d_pos = nullptr; g.d_sub_mat = nullptr;
+        cudaFree(g.d_index); cudaFree(g.d_pos); cudaFree(g.d_sub_mat); cudaFree(g.d_ascii);
+        g.d_index = g.d_pos = nullptr; g.d_sub_mat = nullptr; g.d_ascii = nullptr; g.ascii_cap = 0;
+        if (g.ev_up) cudaEventDestroy(g.ev_up);
+        g.ev_up = nullptr;
         if (g.ctrl) cudaStreamDestroy(g.ctrl);
         g.ctrl = nullptr;
     }
