@@ -204,6 +204,10 @@ int sa_get_stats(sa_stats *out);
 int sa_reset_stats(void);
 /* 1 = record per-phase CUDA events (adds stream syncs; off by default) */
 int sa_set_profiling(int enabled);
+/* SeedAndFilter calls served by each GPU of the pool since sa_reset_stats (the reference hands a call to
+ * whichever GPU is free, src/seed_filter.cu:699-708 / :798-803): out[i] for GPU i, at most cap entries.
+ * Returns the number of GPUs in the pool. */
+int sa_get_gpu_calls(uint64_t *out, int cap);
 
 const char *sa_version(void);
 

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "sa_clear_query", "sa_seed_and_filter", "sa_release_result", "sa_seed_and_filter_range",
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
     "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds", "sa_write_segments",
-    "sa_pipeline_run", "sa_pipeline_plan", "sa_build_matrix",
+    "sa_pipeline_run", "sa_pipeline_plan", "sa_build_matrix", "sa_get_gpu_calls",
 ]
 
 
@@ -114,6 +114,7 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_debug_get_encoded.argtypes = [C.c_int, C.c_uint32, C.c_void_p, C.c_uint32]
     lib.sa_get_stats.argtypes = [C.POINTER(SaStats)]
     lib.sa_set_profiling.argtypes = [C.c_int]
+    lib.sa_get_gpu_calls.argtypes = [C.POINTER(C.c_uint64), C.c_int]
     lib.sa_host_chunk_seeds.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     lib.sa_host_chunk_seeds.restype = C.c_size_t
     lib.sa_write_segments.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64,
@@ -279,6 +280,12 @@ class Backend:
         s = SaStats()
         self._check(self.lib.sa_get_stats(C.byref(s)))
         return s.as_dict()
+
+    def gpu_calls(self) -> list:
+        """SeedAndFilter calls served by each GPU of the pool since reset_stats()."""
+        buf = (C.c_uint64 * 64)()
+        n = self._check(self.lib.sa_get_gpu_calls(buf, 64))
+        return [int(buf[i]) for i in range(min(n, 64))]
 
     def reset_stats(self) -> None:
         self._check(self.lib.sa_reset_stats())

@@ -127,6 +127,7 @@ struct GpuCtx {
     int *d_sub_mat = nullptr;
     uint8_t *d_ascii = nullptr; size_t ascii_cap = 0; // ASCII staging buffer of block uploads
     cudaEvent_t ev_up = nullptr;                      // upload / peer copy of the current block has landed
+    uint64_t calls = 0;                               // SeedAndFilter calls served by this GPU (under stats_mu)
     std::vector<Workspace *> ws;
 };
 
@@ -620,6 +621,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     {
         std::lock_guard<std::mutex> l(G.stats_mu);
         sa_stats &s = G.stats;
+        g.calls++;
         s.calls++; s.seeds += num_seeds; s.hits += num_hits; s.survivors += n_surv;
         s.anchors_pre_dedupe += n_pre; s.hsps += n_final; s.ext_cells += ext_cells;
         s.launches += launches;
@@ -1131,9 +1133,18 @@ int sa_get_stats(sa_stats *out) {
 int sa_reset_stats(void) {
     std::lock_guard<std::mutex> l(G.stats_mu);
     G.stats = sa_stats();
+    for (auto &g : G.gpus) g.calls = 0;
     return SA_OK;
 }
 int sa_set_profiling(int enabled) { G.profiling = enabled != 0; return SA_OK; }
+
+int sa_get_gpu_calls(uint64_t *out, int cap) {
+    if (!out || cap < 0) return fail(SA_ERR_ARG, "out is NULL");
+    std::lock_guard<std::mutex> l(G.stats_mu);
+    const int n = (int)G.gpus.size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = G.gpus[i].calls;
+    return n;
+}
 
 // Host-side seed words of one chunk, the loop of src/seeder.cpp:57-74 with
 // GetKmerIndexAtPos (common/ntcoding.cpp:43-61) restated as a rolling validity window.

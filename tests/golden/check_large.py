@@ -5,11 +5,13 @@
 For each case: oracle/_ref/oracle_runner (the reference's own CUDA kernels rebuilt for sm_100a,
 SURVEY 8d "reference GPU timing") and the new backend run the same SeedAndFilter calls; every
 call's records must be byte-identical; the time both spend inside SeedAndFilter is reported.
-Too slow for the CPU oracle and too big to commit as fixtures -- hence a script, not a test.
+The same cases run as `-m gpu` tests (tests/test_live_reference_gpu.py); this script adds the timing
+columns and runs the self-alignment at full E. coli size (~270 s of reference kernel time).
 """
 from __future__ import annotations
 
 import json
+import os
 import sys
 import tempfile
 import time
@@ -24,50 +26,10 @@ from segalign_b200 import genome  # noqa: E402
 from tests import harness as H  # noqa: E402
 
 
-def gen_ecoli_self(rng):
-    g = genome.random_genome(4_641_652, rng)
-    return g, g.copy()
+os.environ.setdefault("SEGALIGN_LIVE_FULL", "1")   # the self-alignment at E. coli size (the -m gpu test uses 1.2 Mb)
+from tests import test_live_reference_gpu as L  # noqa: E402  (generators + case list live with the test)
 
-
-def gen_ecoli_mut40(rng):
-    g = genome.random_genome(4_641_652, rng)
-    return g, genome.mutate(g, 0.40, rng)
-
-
-def gen_worm_piece(rng):
-    import bench
-    chroms = bench.make_ref(bench.scaled_records(20))
-    ref = genome.make_blocks(chroms)[0]
-    q = genome.make_blocks(bench.make_query(chroms, 0))[0][:3_000_000]
-    return ref, q
-
-
-def gen_chr1_like(rng):
-    """BASELINE configs[3] at reduced size: half soft-masked reference with long N runs, a 30 %-diverged
-    query with shared short N / IUPAC runs (they sit inside HSPs under --ambiguous=iupac) and its own
-    soft-masking; run with --notransition --ambiguous=iupac on the plus strand (IUPAC letters in the
-    query: the reference's host RevComp drops them, see harness.gen_shared_ambiguous)."""
-    n = 6_000_000
-    ref = genome.random_genome(n, rng)
-    q = genome.mutate(ref, 0.30, rng)
-    for s in rng.integers(0, n - 8, size=3000):
-        ref[s:s + 6] = ord("N"); q[s:s + 6] = ord("N")
-    for s in rng.integers(0, n - 8, size=3000):
-        ref[s:s + 2] = ord("R"); q[s:s + 2] = ord("R")
-    ref = genome.insert_runs(genome.soft_mask(ref, 0.5, rng), b"N", 3, 150_000, rng)
-    q = genome.soft_mask(q, 0.45, rng)
-    return ref, q[:4_000_000]
-
-
-H.GENERATORS.update(ecoli_self=gen_ecoli_self, ecoli_mut40=gen_ecoli_mut40, worm_piece=gen_worm_piece,
-                    chr1_like=gen_chr1_like)
-CASES = [
-    H.Case("ecoli_mut40", "ecoli_mut40"),                      # BASELINE configs[0], throughput variant
-    H.Case("worm_piece_20Mb_x_3Mb", "worm_piece"),             # configs[1] at reduced size, soft-masked
-    H.Case("ecoli_self", "ecoli_self"),                        # configs[0]: main-diagonal blow-up (SURVEY 7)
-    H.Case("chr1_like_6Mb_x_4Mb_iupac_notransition", "chr1_like", transition=False, ambiguous="iupac",
-           strand="plus"),                                    # configs[3] flags at reduced size
-]
+CASES = L.LIVE_CASES
 
 
 def main():
