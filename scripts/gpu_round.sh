@@ -1,39 +1,37 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, bench per filter kernel, ncu launch list + full capture of the
-# dominant kernel.  Usage (from the repo root on the box): bash scripts/gpu_round.sh <tag> [kernels...]
-TAG=${1:-rX}; shift
-KERNELS=${@:-3 2}
+# One GPU-box visit: parity tests, the bench on both workloads, ncu launch list + full capture of the
+# dominant kernel.  Usage (from the repo root on the box): bash scripts/gpu_round.sh <tag> [steps]
+# Env: SKIP_TESTS=1, SKIP_NCU=1, FULL_BENCH=1 (reference-GPU leg, secondary workloads, LASTZ baseline),
+#      NCU_WORKLOADS="syn500 ce11"
+TAG=${1:-rX}; STEPS=${2:-3}
 OUT=gpurun_out
 mkdir -p $OUT
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > $OUT/${TAG}_gpu.txt
-timeout 1800 python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
-echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
-tail -3 $OUT/${TAG}_pytest.log
-if [ -n "$CHECK_LARGE" ]; then
-  timeout 900 python tests/golden/check_large.py $CHECK_LARGE > $OUT/${TAG}_check_large.json 2> $OUT/${TAG}_check_large.err
-  echo "check_large exit $?"; cat $OUT/${TAG}_check_large.json | cut -c1-700
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/${TAG}_gpu.txt
+free -g | head -2 >> $OUT/${TAG}_gpu.txt; nproc >> $OUT/${TAG}_gpu.txt
+if [ -z "$SKIP_TESTS" ]; then
+  timeout 1500 python -m pytest tests -m gpu -x -q --durations=12 > $OUT/${TAG}_pytest.log 2>&1
+  echo "pytest exit $?" | tee -a $OUT/${TAG}_pytest.log
+  tail -18 $OUT/${TAG}_pytest.log
 fi
-for K in $KERNELS; do
-  SEGALIGN_B200_FILTER_KERNEL=$K timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline \
-      > $OUT/${TAG}_bench_k$K.json 2> $OUT/${TAG}_bench_k$K.err
-  echo "bench k=$K exit $?"; cat $OUT/${TAG}_bench_k$K.json | cut -c1-600
-done
-if [ -n "$EXTRA_BUILDS" ]; then   # "name:flags;name:flags": rebuild on the box and bench each variant
-  IFS=';' read -ra VARS <<< "$EXTRA_BUILDS"
-  for V in "${VARS[@]}"; do
-    NAME=${V%%:*}; FLAGS=${V#*:}
-    SEGALIGN_B200_NVCC_EXTRA="$FLAGS" python -c "from segalign_b200.build import build_backend; build_backend(force=True)"
-    timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_bench_$NAME.json 2> $OUT/${TAG}_bench_$NAME.err
-    echo "variant $NAME ($FLAGS): $(python -c "import json;d=json.load(open('$OUT/${TAG}_bench_$NAME.json'));print(d['value'],d['ms_per_step'],d['roofline']['avg_launch_ms'],d['e2e']['value'])")"
+LEAN="--no-cpu-baseline --no-reference-gpu --no-extra"
+if [ -n "$FULL_BENCH" ]; then
+  timeout 1500 python bench.py --steps $STEPS --warmup 3 > $OUT/${TAG}_bench_syn500.json 2> $OUT/${TAG}_bench_syn500.err
+else
+  timeout 900 python bench.py --steps $STEPS --warmup 3 $LEAN > $OUT/${TAG}_bench_syn500.json 2> $OUT/${TAG}_bench_syn500.err
+fi
+echo "bench syn500 exit $?"; cut -c1-1500 $OUT/${TAG}_bench_syn500.json; tail -5 $OUT/${TAG}_bench_syn500.err
+timeout 900 python bench.py --workload ce11 --steps $STEPS --warmup 3 $LEAN > $OUT/${TAG}_bench_ce11.json 2> $OUT/${TAG}_bench_ce11.err
+echo "bench ce11 exit $?"; cut -c1-600 $OUT/${TAG}_bench_ce11.json
+if [ -z "$SKIP_NCU" ]; then
+  for W in ${NCU_WORKLOADS:-syn500}; do
+    QMB=8; [ "$W" = "syn500" ] && QMB=4
+    ARGS="--workload $W --steps 1 --warmup 1 $LEAN --query-mb $QMB --roofline-launches 8 --acct-launches 2 --vector-steps 1"
+    timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_${W}_launches.csv \
+        python bench.py $ARGS > $OUT/${TAG}_${W}_ncu_bench.log 2>&1
+    python profiles/launch_summary.py $OUT/${TAG}_${W}_launches.csv > $OUT/${TAG}_${W}_launches_summary.txt; head -8 $OUT/${TAG}_${W}_launches_summary.txt
+    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_filter_hits3 -s 12 -c 2 -f -o $OUT/${TAG}_${W}_filter \
+        python bench.py $ARGS > $OUT/${TAG}_${W}_ncu_full.log 2>&1
+    ncu -i $OUT/${TAG}_${W}_filter.ncu-rep --page raw --csv > $OUT/${TAG}_${W}_filter_raw.csv 2>/dev/null
+    python profiles/ncu_extract.py $OUT/${TAG}_${W}_filter_raw.csv > $OUT/${TAG}_${W}_k_filter_hits3_ncu_summary.txt; cat $OUT/${TAG}_${W}_k_filter_hits3_ncu_summary.txt
   done
-  python -c "from segalign_b200.build import build_backend; build_backend(force=True)"
 fi
-K=${KERNELS%% *}
-export SEGALIGN_B200_FILTER_KERNEL=$K
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --query-mb 8 --roofline-launches 8 > $OUT/${TAG}_ncu_bench.log 2>&1
-python profiles/launch_summary.py $OUT/${TAG}_launches.csv > $OUT/${TAG}_launches_summary.txt; cat $OUT/${TAG}_launches_summary.txt | head -8
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_filter_hits -s 20 -c 2 -f -o $OUT/${TAG}_filter \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --query-mb 8 --roofline-launches 8 > $OUT/${TAG}_ncu_full.log 2>&1
-ncu -i $OUT/${TAG}_filter.ncu-rep --page raw --csv > $OUT/${TAG}_filter_raw.csv 2>/dev/null
-python profiles/ncu_extract.py $OUT/${TAG}_filter_raw.csv > $OUT/${TAG}_filter_ncu_summary.txt; cat $OUT/${TAG}_filter_ncu_summary.txt

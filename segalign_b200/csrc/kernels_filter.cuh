@@ -41,6 +41,9 @@ constexpr uint32_t FILTER_CHUNK = 128;              // hits per warp-level work 
 struct FilterParams {
     const uint4 *rrec;   // reference records, index 0 = first 32 bases (front/back padded)
     const uint4 *qrec;   // query records (forward or reverse-complement block)
+    const uint64_t *rp2;     // reference 2-bit plane (front/back padded like the records): the screen's window
+    const uint32_t *rsoft;   // reference soft-record map, bit (w + REC_FRONT); read only if ref_has_soft
+    int ref_has_soft;
     int xdrop;
     int hspthresh;
     int diag_all_positive;
@@ -501,7 +504,7 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
 // terminators (block boundary).  rec points at record 0.
 __global__ void __launch_bounds__(256)
 k_pack_records(const uint8_t *__restrict__ b8, uint32_t len, uint4 *__restrict__ rec, int front,
-               uint32_t words, uint32_t term_codes) {
+               uint32_t words, uint32_t term_codes, uint32_t *__restrict__ softmap, uint32_t softmap_words) {
     const uint32_t total = words + (uint32_t)front;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -517,7 +520,18 @@ k_pack_records(const uint8_t *__restrict__ b8, uint32_t len, uint4 *__restrict__
             else soft |= 1u << cell;
         }
         rec[w] = make_uint4((uint32_t)bits, (uint32_t)(bits >> 32), term, soft);
+        if (soft) { // rare: IUPAC letters, or N under --ambiguous
+            atomicOr(softmap + (i >> 5), 1u << (i & 31u));
+            atomicAdd(softmap + softmap_words, 1u);
+        }
     }
+}
+
+// "any soft cell in records w-3 .. w+2" of the record that holds cell `anchor` (six consecutive map bits)
+__device__ __forceinline__ bool soft_window(const uint32_t *__restrict__ softmap, uint32_t anchor) {
+    const uint32_t b = (anchor >> 5) + (uint32_t)REC_FRONT - 3u;
+    const uint32_t lo = __ldg(softmap + (b >> 5)), hi = __ldg(softmap + (b >> 5) + 1);
+    return (__funnelshift_r(lo, hi, b & 31u) & 0x3Fu) != 0;
 }
 
 } // namespace sa

@@ -10,9 +10,13 @@
 //   1. query windows are aligned once per seed word (seed vectors) or once per query position
 //      (device seeding: the 13 words of a position share it), not per hit, and kept in shared
 //      memory: all hits of a seed word share the query anchor;
-//   2. the reference window of a hit (6 consecutive records = 96 bytes) is fetched by six
+//   2. the reference window of a hit (6 consecutive words of the bare 2-bit plane = 48 bytes; no
+//      terminator / soft bits travel with it, see screen_align_p2 in screen_bound.h) is fetched by six
 //      neighbouring lanes with cp.async straight into shared memory: a 32-lane request touches
-//      ~9 lines instead of 32, the owner lane then reads its records with conflict-free LDS.128;
+//      ~7 lines instead of 32, the owner lane then reads its words with conflict-free LDS.128.
+//      (Round 1 fetched 16-byte records, 96 bytes per hit: ncu at a 500 Mb reference block showed
+//      15.9 GB of DRAM reads per launch = 163 bytes per hit, 87 % of the measured HBM peak, L2 hit
+//      rate 29 % -- the 250 MB of records did not fit the L2; the 125 MB 2-bit plane does.);
 //   3. the hit is decided by the popcount screen of screen_bound.h (~15 instructions per 16-cell
 //      block, 10 blocks) -- about 98 % of random hits end here;
 //   4. undecided hits are queued per warp and walked by the persistent-lane tile loop of
@@ -31,7 +35,7 @@ namespace sa {
 #define SA_SCR_MIN_CTAS 3
 #endif
 #ifndef SA_SCR_STAGE_STRIDE
-#define SA_SCR_STAGE_STRIDE 7
+#define SA_SCR_STAGE_STRIDE 10
 #endif
 #ifndef SA_SCR_Q_CAP
 #define SA_SCR_Q_CAP 64
@@ -40,7 +44,8 @@ namespace sa {
 #define SA_SCR_L2_HINTS 1 // reference records evict_last, seed positions evict_first (keeps the records L2-resident)
 #endif
 constexpr int SCR_THREADS = SA_SCR_THREADS;
-constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint4 slots per hit in the staging buffer (6 used; 7 = conflict-free LDS.128)
+constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint64 slots per hit in the staging buffer (6 used; 10 = 80 bytes: 16-byte aligned and conflict-free for LDS.128)
+static_assert(SCR_STAGE_STRIDE % 2 == 0 && SCR_STAGE_STRIDE >= 6, "staging slots are read as 16-byte vectors");
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
 constexpr int SCR_RING = 256;        // staged hits per warp (ring, power of two)
 constexpr int SCR_ROWS = 64;         // aligned query rows per warp (ring, power of two)
@@ -56,7 +61,7 @@ constexpr uint32_t SCR_K_MUL = 1u | (16u << 8); // dp2a multipliers of group_sco
 // dynamic shared memory layout of k_filter_hits3 (bytes)
 constexpr size_t SCR_OFF_LUT = 0;
 constexpr size_t SCR_OFF_STAGE = SCR_OFF_LUT + SCR_LUT_WORDS * 4;
-constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STAGE_STRIDE * 16;
+constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STAGE_STRIDE * 8;
 constexpr size_t SCR_OFF_RING = SCR_OFF_ROWS + (size_t)SCR_WARPS * SCR_ROWS * SCR_ROW_STRIDE * 4;
 constexpr size_t SCR_OFF_QUEUE = SCR_OFF_RING + (size_t)SCR_WARPS * SCR_RING * 4;
 constexpr size_t SCR_OFF_RROW = SCR_OFF_QUEUE + (size_t)SCR_WARPS * SCR_Q_CAP * 8;
@@ -68,6 +73,14 @@ static_assert(SCR_Q_DRAIN >= 1 && SCR_Q_CAP >= SCR_Q_DRAIN + 31, "a round may qu
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8_hint(void *smem_dst, const void *gmem_src, uint64_t policy) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(d), "l"(gmem_src), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -140,7 +153,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     const uint32_t mul = P.k_mul, m4 = P.k_m4;
     const int thr = P.hspthresh;
 
-    uint4 *stage = reinterpret_cast<uint4 *>(smem + SCR_OFF_STAGE) + warp * 32 * SCR_STAGE_STRIDE;
+    uint64_t *stage = reinterpret_cast<uint64_t *>(smem + SCR_OFF_STAGE) + warp * 32 * SCR_STAGE_STRIDE;
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem + SCR_OFF_ROWS) + warp * SCR_ROWS * SCR_ROW_STRIDE;
     uint32_t *ring_r = reinterpret_cast<uint32_t *>(smem + SCR_OFF_RING) + warp * SCR_RING;
     uint32_t *myq = reinterpret_cast<uint32_t *>(smem + SCR_OFF_QUEUE) + warp * SCR_Q_CAP * 2;
@@ -149,7 +162,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     // prefix, and (device seeding) the row id of its query position
     uint32_t *ownerdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS;
     uint8_t *ownerrow = reinterpret_cast<uint8_t *>(ownerdelta + 32);
-    const uint4 *rrec_m3 = P.rrec - 3; // record w-3 of a window (REC_FRONT >= 3 records of front padding)
+    const uint64_t *rp2_m3 = P.rp2 - 3; // word w-3 of a window (REC_FRONT >= 3 words of front padding)
 #if SA_SCR_L2_HINTS
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #endif
@@ -166,6 +179,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t row_tail = 0;         // rows handed out so far (monotonic; row id = counter mod 256)
     uint32_t pre_n = 0;            // hits whose records are already requested (the next round)
     uint32_t r_next = 0;           // lane: reference anchor of its hit of that round
+    bool soft_next = false;        // lane: a soft cell lies in that hit's reference records (blocks with soft cells only)
     bool exhausted = false;
     uint32_t acc_hits = 0, acc_seeds = 0, acc_last = 0;
     bool any_hits = false;
@@ -177,8 +191,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
         const uint32_t qpos = SRC == SRC_RANGE ? H.j0 + key / H.per : (uint32_t)__ldg(H.seeds + key);
         return qpos + H.seed_size;
     };
-    // Reference records w-3 .. w+2 of the next round's n hits: six neighbouring lanes per hit, 16
-    // bytes each, straight into the staging buffer.  r_own = this lane's own hit of that round
+    // Reference words w-3 .. w+2 (2-bit plane) of the next round's n hits: six neighbouring lanes per
+    // hit, 8 bytes each, straight into the staging buffer.  r_own = this lane's own hit of that round
     // (anchor in the reference block); the loader lanes get the anchors by shuffle.
     auto request_records = [&](uint32_t r_own, uint32_t n) {
 #pragma unroll
@@ -188,9 +202,9 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             const uint32_t r = __shfl_sync(0xFFFFFFFFu, r_own, hs & 31u);
             if (hs < n) {
 #if SA_SCR_L2_HINTS
-                cp_async16_hint(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc), pol_keep);
+                cp_async8_hint(stage + hs * SCR_STAGE_STRIDE + rc, rp2_m3 + ((r >> 5) + rc), pol_keep);
 #else
-                cp_async16(stage + hs * SCR_STAGE_STRIDE + rc, rrec_m3 + ((r >> 5) + rc));
+                cp_async8(stage + hs * SCR_STAGE_STRIDE + rc, rp2_m3 + ((r >> 5) + rc));
 #endif
             }
         }
@@ -357,6 +371,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 n1 = min(tail - head, 32u);
                 safe_tail = tail;
                 r_next = lane < n1 ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
+                if (P.ref_has_soft) soft_next = lane < n1 && soft_window(P.rsoft, r_next);
                 request_records(r_next, n1);
                 cp_async_commit();
                 cp_async_wait_all();
@@ -378,15 +393,18 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             r0 = r_next; // this lane's anchor: read when the records were requested
             uint32_t rr[SCREEN_ROW_WORDS];
             {
-                const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
-                const ScreenRec a[SCREEN_RECS] = {as_rec(mine[0]), as_rec(mine[1]), as_rec(mine[2]),
-                                                  as_rec(mine[3]), as_rec(mine[4]), as_rec(mine[5])};
-                screen_align(a, r0 & 31u, rr);
+                const uint4 *mine = reinterpret_cast<const uint4 *>(stage + lane * SCR_STAGE_STRIDE);
+                const uint4 m0 = mine[0], m1 = mine[1], m2 = mine[2];
+                const uint64_t a[SCREEN_RECS] = {(uint64_t)m0.x | ((uint64_t)m0.y << 32), (uint64_t)m0.z | ((uint64_t)m0.w << 32),
+                                                 (uint64_t)m1.x | ((uint64_t)m1.y << 32), (uint64_t)m1.z | ((uint64_t)m1.w << 32),
+                                                 (uint64_t)m2.x | ((uint64_t)m2.y << 32), (uint64_t)m2.z | ((uint64_t)m2.w << 32)};
+                screen_align_p2(a, r0 & 31u, soft_next, rr);
             }
             __syncwarp(); // every lane holds its window: the staging buffer is free again
             head += n1;
             pre_n = min(safe_tail - head, 32u); // only positions that are known to have landed
             r_next = lane < pre_n ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
+            if (P.ref_has_soft) soft_next = lane < pre_n && soft_window(P.rsoft, r_next);
             if (pre_n) request_records(r_next, pre_n);
             cp_async_commit(); // group "R": the records of the next round
             int bound; bool decided;

@@ -182,8 +182,9 @@ void add_launches(uint64_t n) {
 // processes on one box, cost tens of milliseconds per block.
 int free_planes(SeqPlanes &p, cudaStream_t st) {
     if (p.b8) CU(cudaFreeAsync(p.b8, st), SA_ERR_FREE);
-    if (p.p2) CU(cudaFreeAsync(p.p2, st), SA_ERR_FREE);
+    if (p.p2_base) CU(cudaFreeAsync(p.p2_base, st), SA_ERR_FREE);
     if (p.m1) CU(cudaFreeAsync(p.m1, st), SA_ERR_FREE);
+    if (p.softmap) CU(cudaFreeAsync(p.softmap, st), SA_ERR_FREE);
     if (p.rec_base) CU(cudaFreeAsync(p.rec_base, st), SA_ERR_FREE);
     p = SeqPlanes();
     return SA_OK;
@@ -193,7 +194,11 @@ int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag, cudaStream_t st) {
     p.len = len;
     p.words = ((size_t)len + 31) / 32 + PAD_WORDS;
     cudaError_t e = cudaMallocAsync((void **)&p.b8, (size_t)len + 64, st);
-    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.p2, p.words * sizeof(uint64_t), st);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.p2_base, (p.words + REC_FRONT) * sizeof(uint64_t), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p.p2_base, 0, REC_FRONT * sizeof(uint64_t), st);
+    p.p2 = p.p2_base ? p.p2_base + REC_FRONT : nullptr;
+    p.softmap_words = (uint32_t)((p.words + REC_FRONT) / 32 + 2);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.softmap, ((size_t)p.softmap_words + 1) * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.m1, p.words * sizeof(uint32_t), st);
     if (e == cudaSuccess) e = cudaMallocAsync((void **)&p.rec_base, (p.words + REC_FRONT + 1) * sizeof(uint4), st);
     p.rec = p.rec_base ? p.rec_base + REC_FRONT : nullptr;
@@ -205,9 +210,16 @@ int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag, cudaStream_t st) {
 
 // filter records of one block under the current terminator set (async on the control stream)
 void build_records(GpuCtx &g, SeqPlanes &p) {
+    cudaMemsetAsync(p.softmap, 0, ((size_t)p.softmap_words + 1) * sizeof(uint32_t), g.ctrl);
     k_pack_records<<<grid_for(p.words + REC_FRONT, 256), 256, 0, g.ctrl>>>(p.b8, p.len, p.rec, REC_FRONT,
-                                                                            (uint32_t)p.words, G.term_codes);
+                                                                            (uint32_t)p.words, G.term_codes, p.softmap, p.softmap_words);
     p.term_codes = G.term_codes;
+}
+// host copy of the block's soft-record count (after the control stream has been awaited)
+int read_soft_flag(SeqPlanes &p) {
+    p.has_soft = 0;
+    if (p.softmap) CU(cudaMemcpy(&p.has_soft, p.softmap + p.softmap_words, sizeof(uint32_t), cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
+    return SA_OK;
 }
 
 // ASCII staging buffer of one GPU (plain cudaMalloc, kept and grown: peer copies read it)
@@ -281,6 +293,7 @@ int upload_block_all_gpus(const char *src, uint32_t len, int slot, const char *t
     for (size_t i = 0; i < n; i++) {
         CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
         CU(cudaStreamSynchronize(G.gpus[i].ctrl), SA_ERR_KERNEL);
+        if (slot < 0) TRY(read_soft_flag(G.gpus[i].ref));
     }
     return SA_OK;
 }
@@ -435,6 +448,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.soft_runs = (((G.term_codes >> L_NT) & 1u) == 0 || ((G.term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
+    F.rp2 = g.ref.p2; F.rsoft = g.ref.softmap; F.ref_has_soft = g.ref.has_soft ? 1 : 0;
     F.xdrop = G.xdrop; F.hspthresh = G.hspthresh; F.diag_all_positive = G.diag_all_positive;
     F.k_mul = 4u | (64u << 8); F.k_m4 = 0x01010101u;
     HitSource H = {};
@@ -767,6 +781,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         for (SeqPlanes *p : all)
             if (p->rec && p->term_codes != G.term_codes) build_records(g, *p);
         CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+        if (g.ref.rec) TRY(read_soft_flag(g.ref));
         for (int k = 0; k < G.ws_per_gpu; k++) {
             Workspace *w = nullptr;
             TRY(make_workspace((int)i, w));

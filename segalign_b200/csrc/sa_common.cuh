@@ -6,9 +6,14 @@
 //        A,C,G,T = 0..3, every other symbol stored as 0
 //   m1 : 1 bit / base, 32 bases per uint32 word; 1 = "not an upper-case A/C/G/T"
 //        (codes L,N,X,E) and also 1 for every padding cell past the end of the block
-//   rec: 16 bytes / 32 bases = {p2 lo, p2 hi, terminator bits, soft bits}: what the filter kernel
-//        reads (one or two 16-byte loads per 32-cell window instead of four scalar loads from two
-//        planes); REC_FRONT records in front and PAD_WORDS behind are pure terminators
+//   rec: 16 bytes / 32 bases = {p2 lo, p2 hi, terminator bits, soft bits}: what the tile walk of the
+//        filter kernels reads (one or two 16-byte loads per 32-cell window instead of four scalar
+//        loads from two planes) and what the query rows of the screen are built from; REC_FRONT records
+//        in front and PAD_WORDS behind are pure terminators
+//   softmap: 1 bit / record, set where the record holds a "soft" cell (non-ACGT, not a terminator
+//        under the current matrix).  The popcount screen reads the REFERENCE window from the bare p2
+//        plane (48 bytes per hit instead of 96: a 500 Mb block is 125 MB and stays L2-resident) and
+//        needs this map only for blocks that have soft cells at all (screen_bound.h)
 // The hot kernels read only p2/m1 (0.375 byte per base instead of 1); b8 is touched by the
 // exact extension only inside 32-base tiles that contain a masked cell.
 #pragma once
@@ -28,8 +33,12 @@ constexpr int REC_FRONT = 4; // padding records in front of record 0 (pure termi
 
 struct SeqPlanes {
     uint8_t *b8 = nullptr;
-    uint64_t *p2 = nullptr;
+    uint64_t *p2_base = nullptr; // p2 allocation: REC_FRONT zero words in front of word 0 (the screen reads words w-3 .. w+2)
+    uint64_t *p2 = nullptr;      // = p2_base + REC_FRONT
     uint32_t *m1 = nullptr;
+    uint32_t *softmap = nullptr; // one bit per record (index w + REC_FRONT): the record holds a soft cell; last word = soft record count
+    uint32_t softmap_words = 0;  // bitmap words (the counter sits at softmap[softmap_words])
+    uint32_t has_soft = 0;       // host copy of the counter: 0 = the screen never has to look at the map
     uint4 *rec_base = nullptr; // filter records {p2 lo, p2 hi, terminator bits, soft bits}, REC_FRONT + words
     uint4 *rec = nullptr;      // = rec_base + REC_FRONT (record 0 = bases 0..31)
     uint32_t term_codes = 0;   // terminator code set the records were built with

@@ -104,6 +104,36 @@ SA_HD void screen_align(const ScreenRec (&a)[SCREEN_RECS], uint32_t sh, uint32_t
     row[11] = 0u;
 }
 
+// The same for the REFERENCE side of a hit from the bare 2-bit plane: a[0..5] = words w-3 .. w+2 of
+// the p2 plane (32 cells per 64-bit word, non-ACGT cells stored as 0).  No terminator or soft bits
+// travel with the window (48 bytes per hit instead of 96):
+//   * terminator cells (and cells past the end of the block) may be ignored altogether.  The
+//     reference's walk stops at the first such cell p (its score is < -xdrop, or the walk runs out of
+//     the block: cells past the end score 0 and end the walk with their tile), so every cell it
+//     scores lies before p, where the stored codes are the true ones: Mhat still bounds its running
+//     maximum, and "stopped by the end of block j" is true for every block that reaches p whatever
+//     the popcounts say.  Ignoring them only loses the shortcut "a terminator in the window proves the
+//     stop"; the X-drop proof fires on the cells behind p as it does on random sequence;
+//   * soft cells (non-ACGT, not a terminator: a real score the stored code 0 would misstate) must
+//     send the hit to the tile walk: `soft` = any soft cell in records w-3 .. w+2, from the block's
+//     one-bit-per-record map (a superset of the window).
+SA_HD void screen_align_p2(const uint64_t (&a)[SCREEN_RECS], uint32_t sh, bool soft, uint32_t (&row)[SCREEN_ROW_WORDS]) {
+    const bool o = sh >= 16u;
+    const uint32_t k = (2u * sh) & 31u;
+    const uint32_t s[12] = {(uint32_t)a[0], (uint32_t)(a[0] >> 32), (uint32_t)a[1], (uint32_t)(a[1] >> 32),
+                            (uint32_t)a[2], (uint32_t)(a[2] >> 32), (uint32_t)a[3], (uint32_t)(a[3] >> 32),
+                            (uint32_t)a[4], (uint32_t)(a[4] >> 32), (uint32_t)a[5], (uint32_t)(a[5] >> 32)};
+    uint32_t t[11];
+#pragma unroll
+    for (int i = 0; i < 11; i++) t[i] = o ? s[i + 1] : s[i];
+#pragma unroll
+    for (int j = 0; j < SCREEN_RB; j++) row[j] = scr_funnel_r(t[6 + j], t[7 + j], k);
+#pragma unroll
+    for (int j = 0; j < SCREEN_LB; j++) row[SCREEN_RB + j] = scr_funnel_r(t[5 - j], t[6 - j], k);
+    row[10] = soft ? (uint32_t)SCREEN_F_SOFT : 0u;
+    row[11] = 0u;
+}
+
 // One direction: NB blocks in walk order.  Returns the bound of the running maximum; proven = the
 // reference's walk stops inside the window by the X-drop rule.
 template <int NB>

@@ -366,3 +366,46 @@ def golden_as_calls(case: Case):
         res[1:] = segs
         out.append((rev, cs, ce, ns, res))
     return out, digest
+
+
+# ------------------------------------------------------------------------------ the reference's segment printer
+SEGPRINT_RUNNER = ROOT / "oracle" / "_ref" / "segprint_runner"
+
+
+def run_reference_printer(workdir: Path, r_table, q_table, rc_table, block, interval, fw, rc, *, data_folder="",
+                          output_format="maf-", ambiguous="", scoring_file="", gapped=True, ydrop=9430,
+                          gappedthresh=3000, notrivial=False):
+    """One printer_input through the UNMODIFIED src/segment_printer.cpp (oracle/_ref/segprint_runner).
+
+    tables = (names, starts, lens) with buffer offsets as src/main.cpp keeps them; block =
+    (r_index [ref block index + 1, main.cpp:611], q_index, r_start, q_start, r_len, q_len [block length -
+    seed size, main.cpp:714]); interval = (start, end, num_invoked).  Returns ({file name: text},
+    [LASTZ command lines])."""
+    workdir.mkdir(parents=True, exist_ok=True)
+    out_dir = workdir / "printer_out"
+    out_dir.mkdir(exist_ok=True)
+    for f in out_dir.glob("*"):
+        f.unlink()
+
+    def s(x):
+        b = x.encode()
+        return struct.pack("<I", len(b)) + b
+
+    def table(t):
+        names, starts, lens = t
+        out = struct.pack("<I", len(names))
+        for n, st, ln in zip(names, starts, lens):
+            out += s(n) + struct.pack("<QI", int(st), int(ln))
+        return out
+    inp = workdir / "printer.in"
+    with open(inp, "wb") as f:
+        f.write(b"SASEG001" + s(data_folder) + s(output_format) + s(ambiguous) + s(scoring_file))
+        f.write(struct.pack("<iiii", int(gapped), ydrop, gappedthresh, int(notrivial)))
+        f.write(table(r_table) + table(q_table) + table(rc_table))
+        f.write(struct.pack("<iiQQII", *[int(v) for v in block]))
+        f.write(struct.pack("<III", *[int(v) for v in interval]))
+        for h in (fw, rc):
+            h = np.ascontiguousarray(h, dtype=SEGMENT_DTYPE)
+            f.write(struct.pack("<I", h.size) + h.tobytes())
+    p = subprocess.run([str(SEGPRINT_RUNNER), str(inp), str(out_dir)], check=True, capture_output=True, text=True)
+    return {q.name: q.read_text() for q in out_dir.glob("*.segments")}, p.stdout.splitlines()

@@ -51,6 +51,20 @@ static void row_of(const Records &R, uint32_t anchor, uint32_t (&row)[SCREEN_ROW
     screen_align(a, anchor & 31u, row);
 }
 
+// the reference side as the kernel sees it since round 2: the bare p2 words of records w-3 .. w+2 plus
+// "any soft cell in those six records" from the one-bit-per-record map; terminator bits are not used
+static void row_of_p2(const Records &R, uint32_t anchor, uint32_t (&row)[SCREEN_ROW_WORDS]) {
+    const int w = (int)(anchor >> 5);
+    uint64_t a[SCREEN_RECS];
+    bool soft = false;
+    for (int i = 0; i < SCREEN_RECS; i++) {
+        const ScreenRec &r = R.at(w - 3 + i);
+        a[i] = (uint64_t)r.x | ((uint64_t)r.y << 32);
+        soft |= r.w != 0;
+    }
+    screen_align_p2(a, anchor & 31u, soft, row);
+}
+
 int main(int argc, char **argv) {
     const unsigned seed = argc > 1 ? (unsigned)atoi(argv[1]) : 1;
     const long n_anchors = argc > 2 ? atol(argv[2]) : 200000;
@@ -105,7 +119,7 @@ int main(int argc, char **argv) {
     const ScreenConsts C = screen_consts_from_matrix(P.sub_mat, xdrop, thresh);
     if (!C.enabled) { printf("screen disabled for this matrix\n"); return 0; }
 
-    long rejected = 0, decided_n = 0, passing = 0, bad = 0;
+    long rejected = 0, decided_n = 0, passing = 0, bad = 0, rejected_full = 0;
     for (long it = 0; it < n_anchors; it++) {
         uint32_t r0, q0;
         const int kind = (int)U(10);
@@ -121,10 +135,20 @@ int main(int argc, char **argv) {
         sao_segment seg;
         const int ok = sao_extend_hit(&P, rb.data(), (uint32_t)RL, qb.data(), (uint32_t)QL, r0, q0, &seg);
         const int exact = ok ? seg.score : 0;
-        uint32_t rr[SCREEN_ROW_WORDS], qr[SCREEN_ROW_WORDS];
-        row_of(RR, r0, rr); row_of(QR, q0, qr);
+        uint32_t rr[SCREEN_ROW_WORDS], qr[SCREEN_ROW_WORDS], rr_full[SCREEN_ROW_WORDS];
+        row_of_p2(RR, r0, rr); row_of(QR, q0, qr);
         int bound; bool decided;
         const bool rej = screen_reject(rr, qr, C, bound, decided);
+        {   // for comparison: the reference window with its terminator / soft bits (16-byte records)
+            row_of(RR, r0, rr_full);
+            int b2; bool d2;
+            const bool rej_full = screen_reject(rr_full, qr, C, b2, d2);
+            if (rej_full) rejected_full++;
+            if ((rej_full && exact >= thresh) || (d2 && b2 < exact)) {
+                if (bad < 10) fprintf(stderr, "VIOLATION (record window) r0=%u q0=%u exact=%d bound=%d\n", r0, q0, exact, b2);
+                bad++;
+            }
+        }
         if (exact >= thresh) passing++;
         if (decided) decided_n++;
         if (rej) rejected++;
@@ -133,6 +157,6 @@ int main(int argc, char **argv) {
             bad++;
         }
     }
-    printf("anchors=%ld decided=%ld rejected=%ld passing=%ld violations=%ld\n", n_anchors, decided_n, rejected, passing, bad);
+    printf("anchors=%ld decided=%ld rejected=%ld passing=%ld violations=%ld rejected_with_record_flags=%ld\n", n_anchors, decided_n, rejected, passing, bad, rejected_full);
     return bad ? 1 : 0;
 }

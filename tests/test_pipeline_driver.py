@@ -118,7 +118,7 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     block_size, interval, chunk = 35_000, 16_000, 7_000
     rep = backend.pipeline_run(tmp_path / "ref.fa", tmp_path / "query.fa", out, seq_block_size=block_size,
                                lastz_interval=interval, wga_chunk=chunk, transition=1, xdrop=910, ydrop=9430,
-                               hspthresh=3000, num_threads=4, data_folder="/data/", gapped=0)
+                               hspthresh=3000, num_threads=4, data_folder="/data/", gapped=0, notrivial=1)
     # ---- independent expectation
     r_blocks = genome.make_blocks(ref_chroms, block_size)
     q_blocks = genome.make_blocks(query_chroms, block_size)
@@ -142,6 +142,10 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     sub = sao.build_matrix("", 910)
     params = sao.make_params(sub, 910, 3000, False, shape.span, 748058112)
     expected, n_intervals = {}, 0
+    printer_files, printer_cmds = {}, []   # the same HSPs through the reference's own segment_printer.cpp
+    use_printer = H.SEGPRINT_RUNNER.exists()
+    (_, _, r_lens), _, _ = _tables(r_blocks, rn)
+    (_, _, q_lens), (_, _, rc_lens), _ = _tables(q_blocks, qn)
     for rb, rblk in enumerate(r_blocks):
         table = sao.Table(shape, rblk, rblk.size, 1)
         ref_enc = sao.encode(rblk)
@@ -151,6 +155,7 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
             q_block_len = qblk.size - shape.span
             for idx, (s, e) in enumerate(genome.interval_list(qblk.size, shape.span, interval), start=1):
                 n_intervals += 1
+                by_strand = []
                 for rev, (lo, hi) in enumerate(((s, e), (q_block_len - e, q_block_len - s))):
                     hsps = []
                     for j0 in range(lo, hi, chunk):
@@ -158,6 +163,14 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
                         if seeds.size:
                             hsps.append(sao.seed_and_filter(params, table, ref_enc, q_rc if rev else q_fwd, seeds)[1:])
                     hsps = np.concatenate(hsps) if hsps else np.empty(0, dtype=H.SEGMENT_DTYPE)
+                    by_strand.append(hsps)
+                    if rev == 1 and use_printer and (by_strand[0].size or by_strand[1].size):
+                        files, cmds = H.run_reference_printer(
+                            tmp_path / "printer", (r_names, r_starts, r_lens), (q_names, q_starts, q_lens),
+                            (rc_names, rc_starts, rc_lens), (rb + 1, qb, r_bstart[rb], q_bstart[qb], rblk.size, q_block_len),
+                            (s, e, idx), by_strand[0], by_strand[1], data_folder="/data/", notrivial=True)
+                        printer_files.update(files)
+                        printer_cmds.extend(cmds)
                     if hsps.size == 0:
                         continue
                     lines = []
@@ -180,6 +193,9 @@ def test_driver_reproduces_blocks_schedule_and_segment_files(backend, tmp_path):
     # one LASTZ command per segments file, in the reference's form (segment_printer.cpp:101-112)
     cmds = (out / "lastz_commands.txt").read_text().splitlines()
     assert len(cmds) == len(expected)
+    if use_printer:   # ... and both, byte for byte, what the reference's unmodified segment_printer.cpp emits
+        assert printer_files == got
+        assert sorted(printer_cmds) == sorted(cmds)
     for c in cmds:
         assert c.startswith("lastz /data/ref.2bit[nameparse=darkspace][multiple][subset=ref_block")
         assert " --format=maf- --ydrop=9430 --gappedthresh=3000 --strand=" in c and " --segments=tmp" in c
