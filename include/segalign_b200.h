@@ -199,6 +199,8 @@ typedef struct sa_stats {
     uint64_t launches;         /* kernels launched by this library */
     uint64_t walked;           /* hits the popcount screen left to the tile walk (0 for the tile-walk-only kernels) */
     uint64_t h2d_bytes;        /* bytes sa_seed_and_filter / sa_send_query actually copied host -> device */
+    uint64_t merge_calls;      /* calls that took the merge pass (more filter survivors than SEGALIGN_B200_MERGE_MIN) */
+    uint64_t merge_dropped;    /* survivors of those calls dropped as provable copies of a neighbour on their diagonal */
 } sa_stats;
 int sa_get_stats(sa_stats *out);
 int sa_reset_stats(void);

@@ -33,7 +33,8 @@ class SaStats(C.Structure):
                [(n, C.c_double) for n in
                 ("ms_h2d", "ms_count_scan", "ms_lookup", "ms_prefilter", "ms_extend", "ms_sort",
                  "ms_d2h", "ms_ref_encode", "ms_table_build", "ms_query_encode")] + \
-               [("launches", C.c_uint64), ("walked", C.c_uint64), ("h2d_bytes", C.c_uint64)]
+               [("launches", C.c_uint64), ("walked", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("merge_calls", C.c_uint64), ("merge_dropped", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -294,7 +294,7 @@ constexpr int EXTEND_THREADS = 32; // one warp per block: fits beside the reside
 // words before the last hit-bearing seed word, 1 from that seed word on.
 __global__ void __launch_bounds__(EXTEND_THREADS)
 k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__restrict__ hits,
-              uint32_t h_end, const SurvRec *__restrict__ surv, uint32_t surv_cap, int surv_ctr, int fused,
+              uint32_t h_end, const SurvRec *__restrict__ surv, uint32_t surv_cap, int surv_ctr, uint32_t merge_min, int fused,
               const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors,
               uint32_t anchor_cap, uint32_t *__restrict__ counters, DedupTable dedup) {
@@ -305,6 +305,7 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
     if (threadIdx.x < 16) lut16[threadIdx.x] = sub_mat[(threadIdx.x >> 2) * 8 + (threadIdx.x & 3)];
     if (threadIdx.x < 4) diag[threadIdx.x] = sub_mat[threadIdx.x * 9];
     __syncthreads();
+    if (surv && merge_min && counters[CTR_SURV] > merge_min) return; // left to the merge pass (kernels_merge.cuh)
     h_end = surv ? min(counters[surv_ctr], surv_cap) : min(plan[1], h_end); // counts known only on the device
     const uint32_t items_per_pass = (gridDim.x * blockDim.x) >> 1;
     const bool left = threadIdx.x & 1u;

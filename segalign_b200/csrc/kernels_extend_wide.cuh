@@ -214,11 +214,13 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
     return DirResult{W.M, W.mp};
 }
 
-// surv[0 .. counters[CTR_SURV]) -> passing HSPs appended to `anchors` (through the duplicate
+// surv[0 .. counters[surv_ctr]) -> passing HSPs appended to `anchors` (through the duplicate
 // table); hits that need the entropy factor -> surv2 (count in counters[CTR_SURV2]).
+// merge_min > 0: a call with more filter survivors than that is left to the merge pass
+// (kernels_merge.cuh) -- the kernel returns at once and the host replays stage B on the representatives.
 __global__ void __launch_bounds__(WIDE_THREADS)
-k_extend_wide(ExtendParams P, const int *__restrict__ sub_mat, const SurvRec *__restrict__ surv, uint32_t surv_cap,
-              SurvRec *__restrict__ surv2, int fused, const uint32_t *__restrict__ hit_bound,
+k_extend_wide(ExtendParams P, const int *__restrict__ sub_mat, const SurvRec *__restrict__ surv, uint32_t surv_cap, int surv_ctr,
+              uint32_t merge_min, SurvRec *__restrict__ surv2, int fused, const uint32_t *__restrict__ hit_bound,
               const uint32_t *__restrict__ plan, Anchor *__restrict__ anchors, uint32_t anchor_cap,
               uint32_t *__restrict__ counters, DedupTable dedup) {
     __shared__ uint32_t lut[WIDE_LUT_WORDS];
@@ -234,7 +236,8 @@ k_extend_wide(ExtendParams P, const int *__restrict__ sub_mat, const SurvRec *__
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lut_lane = (uint32_t)__cvta_generic_to_shared(lut) + (lane & (uint32_t)(WIDE_LUT_COLS - 1)) * 4u;
-    const uint32_t n = min(counters[CTR_SURV], surv_cap);
+    if (merge_min && counters[CTR_SURV] > merge_min) return;
+    const uint32_t n = min(counters[surv_ctr], surv_cap);
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
         const SurvRec rec = surv[i];

@@ -60,6 +60,7 @@ enum { CTR_ANCHORS = 0, CTR_DEDUPE = 1, CTR_EXT_LO = 2, CTR_EXT_HI = 3, CTR_SURV
        CTR_NSEEDS = 9,   // fused sources: number of seed words
        CTR_WALKED = 10,  // k_filter_hits3: hits the popcount screen left undecided (tile-walked)
        CTR_SURV2 = 11,   // k_extend_wide: survivors handed on to k_extend_hits (entropy factor needed)
+       CTR_MERGED = 12,  // k_merge_mark: survivors left after dropping provable copies (kernels_merge.cuh)
        CTR_WORDS = 16 };
 
 // 32 cells starting at cell c (may be negative / past the end: the pads are terminators).

@@ -35,7 +35,7 @@ namespace sa {
 #define SA_SCR_MIN_CTAS 3
 #endif
 #ifndef SA_SCR_STAGE_STRIDE
-#define SA_SCR_STAGE_STRIDE 10
+#define SA_SCR_STAGE_STRIDE 4
 #endif
 #ifndef SA_SCR_Q_CAP
 #define SA_SCR_Q_CAP 64
@@ -44,8 +44,8 @@ namespace sa {
 #define SA_SCR_L2_HINTS 1 // reference records evict_last, seed positions evict_first (keeps the records L2-resident)
 #endif
 constexpr int SCR_THREADS = SA_SCR_THREADS;
-constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint64 slots per hit in the staging buffer (6 used; 10 = 80 bytes: 16-byte aligned and conflict-free for LDS.128)
-static_assert(SCR_STAGE_STRIDE % 2 == 0 && SCR_STAGE_STRIDE >= 6, "staging slots are read as 16-byte vectors");
+constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint4 slots per hit in the staging buffer: four 16-byte chunks, XOR-swizzled
+static_assert(SCR_STAGE_STRIDE == 4, "the swizzle below assumes 64-byte staging rows");
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
 constexpr int SCR_RING = 256;        // staged hits per warp (ring, power of two)
 constexpr int SCR_ROWS = 64;         // aligned query rows per warp (ring, power of two)
@@ -61,7 +61,7 @@ constexpr uint32_t SCR_K_MUL = 1u | (16u << 8); // dp2a multipliers of group_sco
 // dynamic shared memory layout of k_filter_hits3 (bytes)
 constexpr size_t SCR_OFF_LUT = 0;
 constexpr size_t SCR_OFF_STAGE = SCR_OFF_LUT + SCR_LUT_WORDS * 4;
-constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STAGE_STRIDE * 8;
+constexpr size_t SCR_OFF_ROWS = SCR_OFF_STAGE + (size_t)SCR_WARPS * 32 * SCR_STAGE_STRIDE * 16;
 constexpr size_t SCR_OFF_RING = SCR_OFF_ROWS + (size_t)SCR_WARPS * SCR_ROWS * SCR_ROW_STRIDE * 4;
 constexpr size_t SCR_OFF_QUEUE = SCR_OFF_RING + (size_t)SCR_WARPS * SCR_RING * 4;
 constexpr size_t SCR_OFF_RROW = SCR_OFF_QUEUE + (size_t)SCR_WARPS * SCR_Q_CAP * 8;
@@ -153,7 +153,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     const uint32_t mul = P.k_mul, m4 = P.k_m4;
     const int thr = P.hspthresh;
 
-    uint64_t *stage = reinterpret_cast<uint64_t *>(smem + SCR_OFF_STAGE) + warp * 32 * SCR_STAGE_STRIDE;
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + SCR_OFF_STAGE) + warp * 32 * SCR_STAGE_STRIDE;
     uint32_t *rows = reinterpret_cast<uint32_t *>(smem + SCR_OFF_ROWS) + warp * SCR_ROWS * SCR_ROW_STRIDE;
     uint32_t *ring_r = reinterpret_cast<uint32_t *>(smem + SCR_OFF_RING) + warp * SCR_RING;
     uint32_t *myq = reinterpret_cast<uint32_t *>(smem + SCR_OFF_QUEUE) + warp * SCR_Q_CAP * 2;
@@ -162,7 +162,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     // prefix, and (device seeding) the row id of its query position
     uint32_t *ownerdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS;
     uint8_t *ownerrow = reinterpret_cast<uint8_t *>(ownerdelta + 32);
-    const uint64_t *rp2_m3 = P.rp2 - 3; // word w-3 of a window (REC_FRONT >= 3 words of front padding)
+    const uint64_t *rp2_m4 = P.rp2 - 4; // 16-byte aligned start of the plane's front padding (REC_FRONT = 4 words)
+    static_assert(REC_FRONT == 4, "the window fetch below starts at word (w + 1) & ~1 of the padded plane");
 #if SA_SCR_L2_HINTS
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
 #endif
@@ -191,20 +192,28 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
         const uint32_t qpos = SRC == SRC_RANGE ? H.j0 + key / H.per : (uint32_t)__ldg(H.seeds + key);
         return qpos + H.seed_size;
     };
-    // Reference words w-3 .. w+2 (2-bit plane) of the next round's n hits: six neighbouring lanes per
-    // hit, 8 bytes each, straight into the staging buffer.  r_own = this lane's own hit of that round
-    // (anchor in the reference block); the loader lanes get the anchors by shuffle.
+    // Reference words w-3 .. w+2 (2-bit plane, 48 bytes) of the next round's n hits, fetched as 16-byte
+    // chunks with cp.async.cg (L1 bypass: an 8-byte .ca copy allocates an L1 line per miss and the ~27 KB
+    // of L1 left beside the shared memory cannot hold the lines of 24 warps' gathers in flight -- measured
+    // 34 % slower at a 500 Mb block).  The fetch starts at the even word at or below w-3: three chunks when
+    // w-3 is even, four when it is odd; the owner lane drops the leading word again (`par` below).
+    // Four neighbouring lanes per hit; r_own = this lane's own hit of that round (anchor in the reference
+    // block), the loader lanes get the anchors by shuffle.  Chunk c of hit h lands in slot c ^ ((h >> 1) & 3)
+    // of the hit's 64-byte row: writes (two rows per quarter warp) and the owners' reads (same chunk of
+    // eight rows) are both bank-conflict free without padding.
     auto request_records = [&](uint32_t r_own, uint32_t n) {
 #pragma unroll
-        for (uint32_t i = 0; i < SCREEN_RECS; i++) {
-            const uint32_t f = i * 32u + lane;
-            const uint32_t hs = f / SCREEN_RECS, rc = f - hs * SCREEN_RECS;
-            const uint32_t r = __shfl_sync(0xFFFFFFFFu, r_own, hs & 31u);
-            if (hs < n) {
+        for (uint32_t i = 0; i < 4; i++) {
+            const uint32_t hs = i * 8u + (lane >> 2), rc = lane & 3u;
+            const uint32_t r = __shfl_sync(0xFFFFFFFFu, r_own, hs);
+            const uint32_t w1 = (r >> 5) + 1u; // = (w - 3) + REC_FRONT
+            if (hs < n && (rc < 3u || (w1 & 1u))) {
+                const uint64_t *src = rp2_m4 + ((w1 & ~1u) + 2u * rc);
+                uint4 *dst = stage + hs * SCR_STAGE_STRIDE + (rc ^ ((hs >> 1) & 3u));
 #if SA_SCR_L2_HINTS
-                cp_async8_hint(stage + hs * SCR_STAGE_STRIDE + rc, rp2_m3 + ((r >> 5) + rc), pol_keep);
+                cp_async16_hint(dst, src, pol_keep);
 #else
-                cp_async8(stage + hs * SCR_STAGE_STRIDE + rc, rp2_m3 + ((r >> 5) + rc));
+                cp_async16(dst, src);
 #endif
             }
         }
@@ -393,11 +402,17 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             r0 = r_next; // this lane's anchor: read when the records were requested
             uint32_t rr[SCREEN_ROW_WORDS];
             {
-                const uint4 *mine = reinterpret_cast<const uint4 *>(stage + lane * SCR_STAGE_STRIDE);
-                const uint4 m0 = mine[0], m1 = mine[1], m2 = mine[2];
-                const uint64_t a[SCREEN_RECS] = {(uint64_t)m0.x | ((uint64_t)m0.y << 32), (uint64_t)m0.z | ((uint64_t)m0.w << 32),
-                                                 (uint64_t)m1.x | ((uint64_t)m1.y << 32), (uint64_t)m1.z | ((uint64_t)m1.w << 32),
-                                                 (uint64_t)m2.x | ((uint64_t)m2.y << 32), (uint64_t)m2.z | ((uint64_t)m2.w << 32)};
+                const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
+                const uint32_t sw = (lane >> 1) & 3u;
+                const uint4 m0 = mine[0u ^ sw], m1 = mine[1u ^ sw], m2 = mine[2u ^ sw], m3 = mine[3u ^ sw];
+                const uint64_t c[8] = {(uint64_t)m0.x | ((uint64_t)m0.y << 32), (uint64_t)m0.z | ((uint64_t)m0.w << 32),
+                                       (uint64_t)m1.x | ((uint64_t)m1.y << 32), (uint64_t)m1.z | ((uint64_t)m1.w << 32),
+                                       (uint64_t)m2.x | ((uint64_t)m2.y << 32), (uint64_t)m2.z | ((uint64_t)m2.w << 32),
+                                       (uint64_t)m3.x | ((uint64_t)m3.y << 32), (uint64_t)m3.z | ((uint64_t)m3.w << 32)};
+                const bool par = (((r0 >> 5) + 1u) & 1u) != 0; // the fetch started one word below w-3
+                uint64_t a[SCREEN_RECS];
+#pragma unroll
+                for (int j = 0; j < SCREEN_RECS; j++) a[j] = par ? c[j + 1] : c[j];
                 screen_align_p2(a, r0 & 31u, soft_next, rr);
             }
             __syncwarp(); // every lane holds its window: the staging buffer is free again

@@ -30,6 +30,7 @@
 #include "kernels_extend_wide.cuh"
 #include "kernels_filter.cuh"
 #include "kernels_lookup.cuh"
+#include "kernels_merge.cuh"
 #include "kernels_screen.cuh"
 #include "kernels_sort.cuh"
 #include "sa_common.cuh"
@@ -103,6 +104,9 @@ struct Workspace {
     uint2 *d_hits = nullptr; size_t hits_cap = 0;
     SurvRec *d_surv = nullptr; size_t surv_cap = 0;  // filter survivors (anchor pair + key)
     SurvRec *d_surv2 = nullptr; size_t surv2_cap = 0; // survivors k_extend_wide hands on to k_extend_hits
+    SurvRec *d_surv_m = nullptr; size_t surv_m_cap = 0; // merge pass: the representatives (kernels_merge.cuh)
+    unsigned long long *d_mkeys = nullptr; size_t mkeys_cap = 0; // merge pass: sort keys, double buffer
+    uint32_t *d_midx = nullptr; size_t midx_cap = 0;             // merge pass: survivor indices, double buffer
     unsigned long long *d_dedup = nullptr;           // exact-duplicate table: k0[slots], k1[slots], tagbits[slots]
     Anchor *d_anchors_a = nullptr; size_t anchors_a_cap = 0;
     Anchor *d_anchors_b = nullptr; size_t anchors_b_cap = 0;
@@ -150,6 +154,7 @@ struct Global {
     int extend_grid = 0;
     int wide_grid = 0;         // k_extend_wide (warp per hit), SEGALIGN_B200_WIDE=0 sends all survivors to k_extend_hits
     bool use_wide = true;
+    uint32_t merge_min = 65536; // calls with more filter survivors than this take the merge pass (SEGALIGN_B200_MERGE_MIN, 0 = never)
     bool use_compact = true;   // SEGALIGN_B200_COMPACT_SEEDS=0: always copy seed vectors as they are
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
@@ -341,6 +346,7 @@ int make_workspace(int gpu_index, Workspace *&out) {
 void destroy_workspace(Workspace *w) {
     cudaFree(w->d_seeds); cudaFree(w->d_prefix); cudaFree(w->d_limit_pos);
     cudaFree(w->d_hit_bound); cudaFree(w->d_plan); cudaFree(w->d_counters);
+    cudaFree(w->d_surv_m); cudaFree(w->d_mkeys); cudaFree(w->d_midx);
     cudaFree(w->d_hits); cudaFree(w->d_surv); cudaFree(w->d_surv2); cudaFree(w->d_dedup); cudaFree(w->d_anchors_a); cudaFree(w->d_anchors_b);
     cudaFree(w->d_out); cudaFree(w->d_temp); cudaFree(w->d_flags); cudaFree(w->d_excl);
     cudaFreeHost(w->h_small);
@@ -408,6 +414,28 @@ int enqueue_range_seeding(Workspace *w, const SeqPlanes &q, const CallInput &in)
     return SA_OK;
 }
 
+// Merge pass (kernels_merge.cuh): the n filter survivors in w->d_surv sorted by (diagonal, anchor), those
+// connected to their predecessor by an all-match stretch dropped, the rest in w->d_surv_m (count in
+// counters[CTR_MERGED]).  Enqueued on the call's stream; n is known because the first attempt's stage B
+// declined the call and the host has seen its counters.
+int enqueue_merge(Workspace *w, const ExtendParams &P, uint32_t n) {
+    cudaStream_t st = w->stream;
+    TRY(ensure(w->d_surv_m, w->surv_m_cap, n, "merged_survivors"));
+    TRY(ensure(w->d_mkeys, w->mkeys_cap, 2 * (size_t)n, "merge_keys"));
+    TRY(ensure(w->d_midx, w->midx_cap, 2 * (size_t)n, "merge_index"));
+    cub::DoubleBuffer<unsigned long long> dk(w->d_mkeys, w->d_mkeys + n);
+    cub::DoubleBuffer<uint32_t> dv(w->d_midx, w->d_midx + n);
+    size_t bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 64, st), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "sort_temp"));
+    CU(cudaMemsetAsync(w->d_counters + CTR_MERGED, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+    k_merge_keys<<<grid_for(n, 256), 256, 0, st>>>(w->d_surv, n, dk.Current(), dv.Current());
+    CU(cub::DeviceRadixSort::SortPairs(w->d_temp, bytes, dk, dv, (int)n, 0, 64, st), SA_ERR_KERNEL);
+    k_merge_mark<<<grid_for(n, 256), 256, 0, st>>>(P, w->d_surv, dv.Current(), n, w->d_surv_m, w->d_counters);
+    CU(cudaGetLastError(), SA_ERR_KERNEL);
+    return SA_OK;
+}
+
 // One SeedAndFilter call.  Produces the malloc'd result (header + HSPs).
 //
 // Fast path (the filter stage is usable): ONE kernel does seeding (SRC_RANGE) / seed-word reading
@@ -434,6 +462,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     bool fused = filter && G.use_fused;
     bool seeds_ready = in.src == SRC_SEEDS; // seed words in d_seeds, count in d_plan[2]
     bool staged = false;                    // result records already in w->h_out
+    bool merged = false;                    // stage B replays on the representatives of the merge pass
     const uint32_t max_items = in.max_items;
 
     if (!w->d_surv) TRY(ensure(w->d_surv, w->surv_cap, (size_t)1 << 20, "survivors", 1, 1));
@@ -469,12 +498,19 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         const uint32_t surv_cap = (uint32_t)std::min<size_t>(w->surv_cap, 0xFFFFFFFFu);
         const uint32_t anchor_cap = (uint32_t)std::min<size_t>(w->anchors_a_cap, 0xFFFFFFFFu);
         uint32_t hits_cap = 0;
-        CU(cudaMemsetAsync(w->d_counters, 0, CTR_WORDS * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        if (!merged) CU(cudaMemsetAsync(w->d_counters, 0, CTR_WORDS * sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        else { // stage A's counters stay; only what stage B and the finalisation write starts over
+            CU(cudaMemsetAsync(w->d_counters + CTR_ANCHORS, 0, 2 * sizeof(uint32_t), st), SA_ERR_MEMCPY); // + CTR_DEDUPE
+            CU(cudaMemsetAsync(w->d_counters + CTR_OUT, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+            CU(cudaMemsetAsync(w->d_counters + CTR_SURV2, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+        }
         if (D.mask) {
             CU(cudaMemsetAsync(w->d_dedup, 0xFF, (size_t)kDedupSlots * 16, st), SA_ERR_MEMCPY);
             CU(cudaMemsetAsync(D.tagbits, 0, (size_t)kDedupSlots * 4, st), SA_ERR_MEMCPY);
         }
-        if (fused) {
+        if (merged) {
+            // stage A already ran: its survivors were reduced to one representative per all-match chain
+        } else if (fused) {
             H.seeds = w->d_seeds;
             if (G.filter_kernel == 3 && G.screen.enabled) {
                 FilterParams F3 = F;
@@ -524,18 +560,23 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             }
         }
         // 4b. stage B: exact extension of the survivors (seed_filter.cu:762-774)
+        // (a call with more than merge_min survivors is declined here and replayed on the representatives
+        // of the merge pass, see below; only the fused path, whose calls are one dedupe scope pair)
+        const SurvRec *sv = merged ? w->d_surv_m : w->d_surv;
+        const int sv_ctr = merged ? (int)CTR_MERGED : (int)CTR_SURV;
+        const uint32_t decline = (fused && filter && !merged && P.diag_all_positive) ? G.merge_min : 0u;
         if (filter && G.use_wide) {
             // warp-per-hit pass over all survivors; what needs the entropy counters goes on to the lane-pair kernel
             if (w->surv2_cap < w->surv_cap) TRY(ensure(w->d_surv2, w->surv2_cap, w->surv_cap, "survivors2", 1, 1));
-            k_extend_wide<<<G.wide_grid, WIDE_THREADS, 0, st>>>(P, g.d_sub_mat, w->d_surv, surv_cap, w->d_surv2, fused ? 1 : 0,
+            k_extend_wide<<<G.wide_grid, WIDE_THREADS, 0, st>>>(P, g.d_sub_mat, sv, surv_cap, sv_ctr, decline, w->d_surv2, fused ? 1 : 0,
                                                                 w->d_hit_bound, w->d_plan, w->d_anchors_a, anchor_cap, w->d_counters, D);
             k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
-                P, g.d_sub_mat, w->d_hits, hits_cap, w->d_surv2, surv_cap, (int)CTR_SURV2, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
+                P, g.d_sub_mat, w->d_hits, hits_cap, w->d_surv2, surv_cap, (int)CTR_SURV2, 0u, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
                 w->d_anchors_a, anchor_cap, w->d_counters, D);
             launches++;
         } else {
             k_extend_hits<<<G.extend_grid, EXTEND_THREADS, 0, st>>>(
-                P, g.d_sub_mat, w->d_hits, hits_cap, filter ? w->d_surv : nullptr, surv_cap, (int)CTR_SURV, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
+                P, g.d_sub_mat, w->d_hits, hits_cap, filter ? sv : nullptr, surv_cap, sv_ctr, decline, fused ? 1 : 0, w->d_hit_bound, w->d_plan,
                 w->d_anchors_a, anchor_cap, w->d_counters, D);
         }
         pt.mark(PH_EXTEND);
@@ -581,6 +622,12 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         }
         if (n_pre > anchor_cap) { // the anchor list did not fit
             TRY(ensure(w->d_anchors_a, w->anchors_a_cap, n_pre, "hsp_reduced"));
+            continue;
+        }
+        if (decline && n_surv > decline) { // stage B declined the call: drop the provable copies, replay stage B
+            TRY(enqueue_merge(w, P, n_surv));
+            launches += 2 + 2 * 8;
+            merged = true;
             continue;
         }
         break;
@@ -640,6 +687,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         s.anchors_pre_dedupe += n_pre; s.hsps += n_final; s.ext_cells += ext_cells;
         s.launches += launches;
         s.walked += n_walked;
+        if (merged) { s.merge_calls++; s.merge_dropped += n_surv - std::min(n_surv, w->h_small[CTR_MERGED]); }
         if (pt.on) {
             s.ms_h2d += ph_ms[PH_SEEDS];
             s.ms_count_scan += ph_ms[PH_PLAN];
@@ -775,6 +823,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         G.wide_grid = 4 * std::max(1, sms);   // four-warp blocks, one warp per hit
         if (const char *e = getenv("SEGALIGN_B200_WIDE_CTAS")) if (atoi(e) > 0) G.wide_grid = atoi(e) * std::max(1, sms);
         { const char *e = getenv("SEGALIGN_B200_WIDE"); G.use_wide = !(e && atoi(e) == 0); }
+        { const char *e = getenv("SEGALIGN_B200_MERGE_MIN"); G.merge_min = e ? (uint32_t)strtoul(e, nullptr, 10) : 65536u; }
         { const char *e = getenv("SEGALIGN_B200_COMPACT_SEEDS"); G.use_compact = !(e && atoi(e) == 0); }
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};

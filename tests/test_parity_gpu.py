@@ -341,3 +341,36 @@ def test_dropin_runner_with_reference_host_objects(name, tmp_path, built):
         res[1:] = segs
         got.append((rev, cs, ce, ns, res))
     H.assert_calls_equal(got, want, "new_runner (reference host objects + shim) vs reference golden")
+
+
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+@pytest.mark.parametrize("device_seeding", [False, True], ids=["vector", "range"])
+def test_merge_pass_matches_reference_golden(backend, case, device_seeding, monkeypatch):
+    """SEGALIGN_B200_MERGE_MIN=8: (almost) every call takes the merge pass of kernels_merge.cuh -- survivors
+    sorted by (diagonal, anchor), those joined to their predecessor by an all-match stretch dropped as
+    provable copies, stage B replayed on the rest.  Must be result-neutral on every golden case."""
+    monkeypatch.setenv("SEGALIGN_B200_MERGE_MIN", "8")
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=device_seeding)
+    H.assert_calls_equal(got, want, "merge pass vs reference golden")
+
+
+def test_merge_pass_collapses_a_self_alignment(backend, monkeypatch):
+    """The main diagonal of a self-alignment is one all-match chain: with the merge pass its hits are
+    extended once per call instead of once per hit, and the records stay those of the reference."""
+    monkeypatch.setenv("SEGALIGN_B200_MERGE_MIN", "1000")
+    case = H.CASES_BY_NAME["self_align"]
+    want, _ = H.golden_as_calls(case)
+    ref, query = case.inputs()
+    span, _ = H.setup_backend(backend, case, ref, query)
+    backend.reset_stats()
+    got = []
+    for rev, j0, j1 in H.chunk_calls(case, query.size, span):
+        res, ns = backend.SeedAndFilterRange(j0, j1, case.transition, bool(rev), 0)
+        if ns:
+            got.append((rev, j0, j1, ns, res))
+    st = backend.stats()
+    H.assert_calls_equal(got, want, "self-alignment through the merge pass vs reference golden")
+    assert st["merge_calls"] >= 1
+    # ~30 k main-diagonal survivors on the plus strand collapse to a handful of representatives
+    assert st["merge_dropped"] > 0.9 * (query.size - span)
