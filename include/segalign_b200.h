@@ -107,6 +107,28 @@ int sa_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint3
                        sa_segment **out, uint32_t *out_count);
 void sa_release_result(sa_segment *out);
 
+/* ---- repeat-masker variant (segalign_repeat_masker) -------------------------------------
+ * repeat_masker_src/seed_filter.h:5-14: the same backend boundary with three signatures changed.  One
+ * sequence block is aligned against itself (plus strand) and against its own reverse complement, which
+ * the backend builds on the device (minus strand).  InitializeInterface / InitializeProcessor /
+ * SendRefWriteRequest / GenerateSeedPosTable / ClearRef / ShutdownProcessor are the calls above. */
+/* SendQueryWriteRequest() -- repeat_masker_src/seed_filter.cu:951-961.  Call after sa_send_ref. */
+int sa_rm_send_query(void);
+/* ClearQuery() -- repeat_masker_src/seed_filter.cu:963-971 */
+int sa_rm_clear_query(void);
+/* SeedAndFilter(seed_offset_vector, rev, ref_start, ref_end) -- repeat_masker_src/seed_filter.cu:724-870.
+ * Seed hits whose reference anchor (position + seed span) lies outside [ref_start, ref_end] are counted
+ * but not extended (:239-244); minus-strand records come back in forward coordinates (:705-709); the
+ * records of an iteration are ordered and thinned by the three-sort / two-unique chain of :819-835.
+ * out[0] = header {ref_start, query_start} = low / high word of the 64-bit hit total, {len, score} =
+ * low / high word of the anchor total (:856-861); out[1..] = records.  Release with sa_release_result. */
+int sa_rm_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint32_t ref_start, uint32_t ref_end,
+                          sa_segment **out, uint32_t *out_count);
+/* The same call with the seed words of positions [q_start, q_end) of the block (rev = 0) or of its reverse
+ * complement (rev = 1) generated on the device (repeat_masker_src/seeder.cpp:69-150 builds them on the host). */
+int sa_rm_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev, uint32_t ref_start,
+                                uint32_t ref_end, sa_segment **out, uint32_t *out_count, uint32_t *out_num_seeds);
+
 /* Device-side seeding: generates the seed words of src/seeder.cpp:57-74 for
  * query positions [q_start, q_end) of the resident (fwd or rev-comp) query block on the GPU,
  * then runs the same pipeline as sa_seed_and_filter.  *out_num_seeds (optional) receives the

@@ -546,4 +546,172 @@ sao_segment *sao_seed_and_filter(const sao_params *p, const sao_table *t, const 
     return out;
 }
 
+/* ------------------------------------------------------------------ repeat-masker variant
+ *
+ * repeat_masker_src/seed_filter.cu: the sequence block is aligned against itself (plus strand) or
+ * against its own reverse complement built on the device (:138-168, :951-961); hits whose reference
+ * anchor lies outside the caller's window [ref_start, ref_end] are enumerated and counted but not
+ * extended (:239-244, :305-310, :328-333); minus-strand records are mapped back to forward coordinates
+ * (:705-709); three sorts and two unique passes (:819-835); 64-bit hit and anchor totals in the
+ * header (:856-861). */
+
+void sao_rm_revcomp_codes(const uint8_t *src, uint32_t len, uint8_t *dst) {
+    /* :138-168 rev_comp_string: on the 8-symbol codes, A<->T, C<->G, every other code unchanged */
+    for (uint32_t i = 0; i < len; i++) {
+        uint8_t c = src[i], r = c;
+        if (c == 0) r = 3; else if (c == 1) r = 2; else if (c == 2) r = 1; else if (c == 3) r = 0;
+        dst[len - 1 - i] = r;
+    }
+}
+
+static int rm_cmp_hspComp(const void *a, const void *b) {
+    /* :109-135: (query_start, len desc, ref_start, score desc) -- all four fields: a total order */
+    const sao_segment *x = (const sao_segment *)a, *y = (const sao_segment *)b;
+    if (x->query_start != y->query_start) return x->query_start < y->query_start ? -1 : 1;
+    if (x->len != y->len) return x->len > y->len ? -1 : 1;
+    if (x->ref_start != y->ref_start) return x->ref_start < y->ref_start ? -1 : 1;
+    if (x->score != y->score) return x->score > y->score ? -1 : 1;
+    return 0;
+}
+static int rm_hspEqual(const sao_segment *x, const sao_segment *y) {
+    /* :79-84 */
+    return x->ref_start == y->ref_start && x->query_start == y->query_start && x->len == y->len && x->score == y->score;
+}
+static int rm_less_hspDiagComp(const sao_segment *x, const sao_segment *y) {
+    /* :52-77: (diagonal [u32 wrap-around], ref_start, query_start, score desc) */
+    uint32_t dx = diag_of(x), dy = diag_of(y);
+    if (dx != dy) return dx < dy;
+    if (x->ref_start != y->ref_start) return x->ref_start < y->ref_start;
+    if (x->query_start != y->query_start) return x->query_start < y->query_start;
+    return x->score > y->score;
+}
+static int rm_less_hspFinalComp(const sao_segment *x, const sao_segment *y) {
+    /* :86-107: (query_start, score desc, ref_start desc) */
+    if (x->query_start != y->query_start) return x->query_start < y->query_start;
+    if (x->score != y->score) return x->score > y->score;
+    return x->ref_start > y->ref_start;
+}
+/* thrust::stable_sort: bottom-up merge sort, equal elements keep their order */
+static void stable_sort_seg(sao_segment *a, size_t n, int (*less)(const sao_segment *, const sao_segment *)) {
+    if (n < 2) return;
+    sao_segment *tmp = (sao_segment *)malloc(n * sizeof(sao_segment));
+    sao_segment *src = a, *dst = tmp;
+    for (size_t w = 1; w < n; w *= 2) {
+        for (size_t lo = 0; lo < n; lo += 2 * w) {
+            size_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n;
+            size_t i = lo, j = mid, k = lo;
+            while (i < mid && j < hi) dst[k++] = less(&src[j], &src[i]) ? src[j++] : src[i++];
+            while (i < mid) dst[k++] = src[i++];
+            while (j < hi) dst[k++] = src[j++];
+        }
+        sao_segment *t = src; src = dst; dst = t;
+    }
+    if (src != a) memcpy(a, src, n * sizeof(sao_segment));
+    free(tmp);
+}
+
+size_t sao_rm_sort_dedupe(sao_segment *a, size_t n) {
+    /* :819-835 */
+    if (n == 0) return 0;
+    qsort(a, n, sizeof(sao_segment), rm_cmp_hspComp);            /* :819 (total order: stability moot) */
+    sao_segment *tmp = (sao_segment *)malloc(n * sizeof(sao_segment));
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)                                /* :821 unique_copy(hspEqual): predecessor in the input */
+        if (i == 0 || !rm_hspEqual(&a[i - 1], &a[i])) tmp[m++] = a[i];
+    stable_sort_seg(tmp, m, rm_less_hspDiagComp);                 /* :825 */
+    size_t k = 0;
+    for (size_t i = 0; i < m; i++)                                /* :827 unique_copy(hspDiagEqual) */
+        if (i == 0 || !hspEqual(&tmp[i - 1], &tmp[i])) a[k++] = tmp[i];
+    stable_sort_seg(a, k, rm_less_hspFinalComp);                  /* :833 */
+    free(tmp);
+    return k;
+}
+
+static uint32_t lower_bound_u64(const uint64_t *a, uint32_t n, uint64_t v) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + (hi - lo) / 2;
+        if (a[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+sao_segment *sao_rm_seed_and_filter(const sao_params *p, const sao_table *t, const uint8_t *seq,
+                                    const uint8_t *seq_rc, uint32_t len, const uint64_t *seeds,
+                                    uint32_t num_seeds, int rev, uint32_t ref_start, uint32_t ref_end, size_t *out_n) {
+    /* :756-758 bucket sizes + inclusive scan, 64-bit */
+    uint64_t *prefix = (uint64_t *)malloc((size_t)(num_seeds ? num_seeds : 1) * sizeof(uint64_t));
+    uint64_t acc = 0;
+    for (uint32_t i = 0; i < num_seeds; i++) {
+        uint32_t seed = (uint32_t)(seeds[i] >> 32);
+        uint32_t n = t->index[seed];
+        if (seed > 0) n -= t->index[seed - 1];
+        acc += n;
+        prefix[i] = acc;
+    }
+    const uint64_t num_hits = num_seeds ? prefix[num_seeds - 1] : 0;
+    /* :760-790 iteration plan (same rule as sao_iteration_plan, 64-bit; same definition of its UB zone) */
+    uint32_t num_iter = 0;
+    uint64_t *limit_pos = (uint64_t *)malloc(((size_t)(p->max_hits ? num_hits / p->max_hits : 0) + 2) * sizeof(uint64_t));
+    if (num_hits > 0) {
+        uint64_t iter_hit_limit;
+        if (num_hits < p->max_hits) { num_iter = 2; iter_hit_limit = num_hits; }
+        else { num_iter = (uint32_t)(num_hits / p->max_hits + 2); iter_hit_limit = p->max_hits; }
+        for (uint32_t i = 0; i + 1 < num_iter; i++) {
+            uint64_t pos = (uint64_t)lower_bound_u64(prefix, num_seeds, iter_hit_limit) - 1;
+            limit_pos[i] = pos;
+            uint64_t base = (pos == (uint64_t)-1) ? 0 : prefix[pos];
+            iter_hit_limit = base + p->max_hits;
+            if (iter_hit_limit > num_hits) iter_hit_limit = num_hits;
+        }
+        limit_pos[num_iter - 1] = num_seeds - 1;
+        if (limit_pos[num_iter - 1] == limit_pos[num_iter - 2]) num_iter--;
+    }
+    const uint8_t *qry = rev ? seq_rc : seq; /* :805-810 */
+    size_t cap = 1024, n_out = 1;
+    sao_segment *out = (sao_segment *)malloc(cap * sizeof(sao_segment));
+    uint64_t total_anchors = 0;
+    uint32_t start_seed = 0;
+    for (uint32_t it = 0; it < num_iter; it++) {
+        uint32_t end_seed = (uint32_t)(limit_pos[it] + 1);
+        size_t acap = 1024, an = 0;
+        sao_segment *anch = (sao_segment *)malloc(acap * sizeof(sao_segment));
+        for (uint32_t s = start_seed; s < end_seed; s++) {
+            uint32_t seed = (uint32_t)(seeds[s] >> 32);
+            uint32_t q0 = (uint32_t)(seeds[s] & 0xFFFFFFFFu) + p->seed_size;
+            uint32_t end = t->index[seed];
+            uint32_t start = seed > 0 ? t->index[seed - 1] : 0;
+            for (uint32_t e = start; e < end; e++) {
+                uint32_t r0 = t->pos[e] + p->seed_size;
+                if (!(r0 >= ref_start && r0 <= ref_end)) continue; /* :239-244: score = -1, never extended */
+                sao_segment seg;
+                if (sao_extend_hit(p, seq, len, qry, len, r0, q0, &seg)) {
+                    if (rev) seg.query_start = len - 1 - (seg.query_start + seg.len); /* :705-709 */
+                    if (an == acap) { acap *= 2; anch = (sao_segment *)realloc(anch, acap * sizeof(sao_segment)); }
+                    anch[an++] = seg;
+                }
+            }
+        }
+        size_t kept = sao_rm_sort_dedupe(anch, an);
+        if (n_out + kept > cap) {
+            while (n_out + kept > cap) cap *= 2;
+            out = (sao_segment *)realloc(out, cap * sizeof(sao_segment));
+        }
+        memcpy(out + n_out, anch, kept * sizeof(sao_segment));
+        n_out += kept;
+        total_anchors += kept;
+        free(anch);
+        start_seed = end_seed;
+    }
+    /* :856-861 */
+    out[0].ref_start = (uint32_t)(num_hits & 0xFFFFFFFFu);
+    out[0].query_start = (uint32_t)(num_hits >> 32);
+    out[0].len = (uint32_t)(total_anchors & 0xFFFFFFFFu);
+    out[0].score = (int32_t)(total_anchors >> 32);
+    free(prefix);
+    free(limit_pos);
+    *out_n = n_out;
+    return out;
+}
+
 void sao_free(void *p) { free(p); }

@@ -105,6 +105,18 @@ int sao_iteration_plan(const uint32_t *prefix, uint32_t num_seeds, uint32_t max_
 /* src/seed_filter.cu:776-782 applied to n records in place; returns the surviving count. */
 size_t sao_sort_dedupe(sao_segment *a, size_t n);
 
+/* ---- repeat-masker variant (repeat_masker_src/seed_filter.cu) ---- */
+/* :138-168 reverse complement on the 8-symbol codes (what SendQueryWriteRequest() builds on the device) */
+void sao_rm_revcomp_codes(const uint8_t *src, uint32_t len, uint8_t *dst);
+/* :819-835 applied to n records in place; returns the surviving count */
+size_t sao_rm_sort_dedupe(sao_segment *a, size_t n);
+/* :724-870: one SeedAndFilter(seeds, rev, ref_start, ref_end) call of the repeat masker.  seq / seq_rc =
+ * the encoded block and its device-style reverse complement.  Header (element 0): ref_start/query_start
+ * = low/high word of the 64-bit hit total, len/score = low/high word of the anchor total. */
+sao_segment *sao_rm_seed_and_filter(const sao_params *p, const sao_table *t, const uint8_t *seq,
+                                    const uint8_t *seq_rc, uint32_t len, const uint64_t *seeds,
+                                    uint32_t num_seeds, int rev, uint32_t ref_start, uint32_t ref_end, size_t *out_n);
+
 void sao_free(void *p);
 
 #ifdef __cplusplus

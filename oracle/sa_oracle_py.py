@@ -63,6 +63,13 @@ def _load() -> C.CDLL:
     lib.sao_iteration_plan.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.sao_sort_dedupe.argtypes = [C.c_void_p, C.c_size_t]
     lib.sao_sort_dedupe.restype = C.c_size_t
+    lib.sao_rm_revcomp_codes.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    lib.sao_rm_revcomp_codes.restype = None
+    lib.sao_rm_sort_dedupe.argtypes = [C.c_void_p, C.c_size_t]
+    lib.sao_rm_sort_dedupe.restype = C.c_size_t
+    lib.sao_rm_seed_and_filter.argtypes = [C.POINTER(SaoParams), C.POINTER(SaoTable), C.c_void_p, C.c_void_p, C.c_uint32,
+                                           C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
+    lib.sao_rm_seed_and_filter.restype = C.c_void_p
     lib.sao_free.argtypes = [C.c_void_p]
     lib.sao_free.restype = None
     return lib
@@ -195,3 +202,30 @@ def sort_dedupe(segs) -> np.ndarray:
     a = np.ascontiguousarray(segs, dtype=SEGMENT_DTYPE).copy()
     n = lib().sao_sort_dedupe(a.ctypes.data, a.size)
     return a[:n]
+
+
+# ---- repeat-masker variant (repeat_masker_src/seed_filter.cu)
+def rm_revcomp_codes(enc) -> np.ndarray:
+    enc = _u8(enc)
+    out = np.empty(enc.size, dtype=np.uint8)
+    lib().sao_rm_revcomp_codes(enc.ctypes.data, enc.size, out.ctypes.data)
+    return out
+
+
+def rm_sort_dedupe(segs) -> np.ndarray:
+    a = np.ascontiguousarray(segs, dtype=SEGMENT_DTYPE).copy()
+    n = lib().sao_rm_sort_dedupe(a.ctypes.data, a.size)
+    return a[:n]
+
+
+def rm_seed_and_filter(params: SaoParams, table: Table, seq_enc, seq_rc_enc, seeds, rev: bool, ref_start: int,
+                       ref_end: int) -> np.ndarray:
+    seq_enc, seq_rc_enc = _u8(seq_enc), _u8(seq_rc_enc)
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    n = C.c_size_t()
+    p = lib().sao_rm_seed_and_filter(C.byref(params), C.byref(table.c), seq_enc.ctypes.data, seq_rc_enc.ctypes.data,
+                                     seq_enc.size, seeds.ctypes.data, seeds.size, int(rev), ref_start, ref_end, C.byref(n))
+    out = np.empty(n.value, dtype=SEGMENT_DTYPE)
+    C.memmove(out.ctypes.data, p, n.value * 16)
+    lib().sao_free(p)
+    return out

@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "sa_shutdown_processor", "sa_debug_get_table", "sa_debug_get_encoded", "sa_get_stats",
     "sa_reset_stats", "sa_set_profiling", "sa_version", "sa_host_chunk_seeds", "sa_write_segments",
     "sa_pipeline_run", "sa_pipeline_plan", "sa_build_matrix", "sa_get_gpu_calls",
+    "sa_rm_send_query", "sa_rm_clear_query", "sa_rm_seed_and_filter", "sa_rm_seed_and_filter_range",
 ]
 
 
@@ -116,6 +117,10 @@ def load_library(path: Path | None = None) -> C.CDLL:
     lib.sa_get_stats.argtypes = [C.POINTER(SaStats)]
     lib.sa_set_profiling.argtypes = [C.c_int]
     lib.sa_get_gpu_calls.argtypes = [C.POINTER(C.c_uint64), C.c_int]
+    lib.sa_rm_seed_and_filter.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    lib.sa_rm_seed_and_filter_range.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.sa_host_chunk_seeds.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
     lib.sa_host_chunk_seeds.restype = C.c_size_t
     lib.sa_write_segments.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64,
@@ -225,6 +230,26 @@ class Backend:
         self._check(self.lib.sa_write_segments(str(path).encode(), hsps.ctypes.data, hsps.size, int(minus),
                                                r_block_start, q_block_start, C.byref(ref_chroms),
                                                C.byref(query_chroms)))
+
+    # --- repeat-masker variant (repeat_masker_src/seed_filter.h:5-14) ---------------------
+    def RmSendQueryWriteRequest(self) -> None:
+        self._check(self.lib.sa_rm_send_query())
+
+    def RmClearQuery(self) -> None:
+        self._check(self.lib.sa_rm_clear_query())
+
+    def RmSeedAndFilter(self, seed_offset_vector: np.ndarray, rev: bool, ref_start: int, ref_end: int) -> np.ndarray:
+        seeds = np.ascontiguousarray(seed_offset_vector, dtype=np.uint64)
+        out, n = C.c_void_p(), C.c_uint32()
+        self._check(self.lib.sa_rm_seed_and_filter(seeds.ctypes.data, seeds.size, int(rev), ref_start, ref_end,
+                                                   C.byref(out), C.byref(n)))
+        return self._take(out, n)
+
+    def RmSeedAndFilterRange(self, q_start: int, q_end: int, transition: bool, rev: bool, ref_start: int, ref_end: int):
+        out, n, ns = C.c_void_p(), C.c_uint32(), C.c_uint32()
+        self._check(self.lib.sa_rm_seed_and_filter_range(q_start, q_end, int(transition), int(rev), ref_start, ref_end,
+                                                         C.byref(out), C.byref(n), C.byref(ns)))
+        return self._take(out, n), ns.value
 
     def ShutdownProcessor(self) -> None:
         self._check(self.lib.sa_shutdown_processor())

@@ -314,7 +314,7 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
     const uint32_t n_pass = (h_end + items_per_pass - 1) / items_per_pass;
     for (uint32_t pass = 0; pass < n_pass; pass++) {
         const uint32_t i = pass * items_per_pass + ((blockIdx.x * blockDim.x + threadIdx.x) >> 1);
-        const bool valid = i < h_end;
+        bool valid = i < h_end;
         uint32_t h = 0;
         uint2 hit = make_uint2(0, 0);
         DirResult D = {0, 0};
@@ -324,7 +324,8 @@ k_extend_hits(ExtendParams P, const int *__restrict__ sub_mat, const uint2 *__re
         if (valid) {
             if (surv) { const SurvRec rec = surv[i]; h = rec.key; hit = make_uint2(rec.r0, rec.q0); }
             else { h = i; hit = hits[i]; }
-            D = extend_dir(P, sub, lut16, diag, hit.x, hit.y, left, C, &cells);
+            valid = hit.x - P.win_lo <= P.win_hi - P.win_lo; // repeat-masker variant: outside the reference window
+            if (valid) D = extend_dir(P, sub, lut16, diag, hit.x, hit.y, left, C, &cells);
         }
         // the right lane (even) receives the left lane's result
         DirResult L;

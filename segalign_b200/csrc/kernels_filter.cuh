@@ -61,6 +61,7 @@ enum { CTR_ANCHORS = 0, CTR_DEDUPE = 1, CTR_EXT_LO = 2, CTR_EXT_HI = 3, CTR_SURV
        CTR_WALKED = 10,  // k_filter_hits3: hits the popcount screen left undecided (tile-walked)
        CTR_SURV2 = 11,   // k_extend_wide: survivors handed on to k_extend_hits (entropy factor needed)
        CTR_MERGED = 12,  // k_merge_mark: survivors left after dropping provable copies (kernels_merge.cuh)
+       CTR_NHITS64 = 14, // (two words, 8-byte aligned) 64-bit hit total of the call: the repeat-masker header needs it
        CTR_WORDS = 16 };
 
 // 32 cells starting at cell c (may be negative / past the end: the pads are terminators).
@@ -134,6 +135,9 @@ struct HitSource {
     const uint32_t *index_table;
     const uint32_t *pos_table;
     uint32_t seed_size;
+    // repeat-masker variant: only hits whose reference anchor lies in [win_lo, win_hi] are extended; the others
+    // are enumerated and counted like any hit (repeat_masker_src/seed_filter.cu:239-244).  0 .. 0xFFFFFFFF otherwise.
+    uint32_t win_lo, win_hi;
     uint32_t index_size;       // 4^weight: seed words with a larger k-mer field are treated as empty buckets
     uint32_t query_len;        // seed words whose span runs past the query block likewise (caller-supplied vectors)
     // SRC_RANGE: seed words of src/seeder.cpp:57-74 generated on the fly
@@ -380,13 +384,14 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
         // ---------------- phase 1: 32 fresh hits, straight-line right 0 / left 0 / left 1
         if (fresh) {
             const uint32_t n1 = min(limit - cursor, 32u);
-            const bool have = lane < n1;
+            bool have = lane < n1;
             uint32_t r0 = 0, q0 = 0, key = 0;
             if (have) {
                 const uint32_t slot = cursor + lane;
                 const uint2 hit = mybuf[slot];
                 r0 = hit.x; q0 = hit.y;
                 key = key_base + (SRC == SRC_HITS ? slot : (uint32_t)myown[slot]);
+                have = r0 - H.win_lo <= H.win_hi - H.win_lo; // outside the caller's reference window: counted, not extended
             }
             cursor += n1;
             // records w0-2 .. w0+1 cover [r0-64, r0+32); the three windows share the cell offset r0 & 31
@@ -493,7 +498,10 @@ k_filter_hits2(FilterParams P, HitSource H, const int *__restrict__ sub_mat, Sur
     }
     if (ext_tiles) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), 32ull * ext_tiles);
     if (SRC != SRC_HITS && lane == 0) {
-        if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits);
+        if (acc_hits) {
+            atomicAdd(counters + CTR_NHITS, acc_hits);
+            atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_NHITS64), (unsigned long long)acc_hits);
+        }
         if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
         if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
     }

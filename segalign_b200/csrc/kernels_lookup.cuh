@@ -22,9 +22,11 @@ struct SeedBounds {
 };
 __global__ void __launch_bounds__(256)
 k_count_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint32_t *__restrict__ d_num_seeds,
-             const uint32_t *__restrict__ index_table, SeedBounds B, uint32_t *__restrict__ counts) {
+             const uint32_t *__restrict__ index_table, SeedBounds B, uint32_t *__restrict__ counts,
+             unsigned long long *__restrict__ total64) {
     const uint32_t num_seeds = min(*d_num_seeds, max_items);
     const uint32_t stride = gridDim.x * blockDim.x;
+    unsigned long long mine = 0;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < max_items; s += stride) {
         uint32_t n = 0;
         if (s < num_seeds && B.ok(seeds[s])) {
@@ -33,7 +35,11 @@ k_count_hits(const uint64_t *__restrict__ seeds, uint32_t max_items, const uint3
             if (kmer > 0) n -= __ldg(index_table + kmer - 1);
         }
         counts[s] = n;
+        mine += n;
     }
+    // 64-bit total beside the uint32 scan (the repeat masker reports it, repeat_masker_src/seed_filter.cu:856-857)
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xFFFFFFFFu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(total64, mine);
 }
 
 // Seed words from their base words.  The reference's seeder emits, per query position, the exact

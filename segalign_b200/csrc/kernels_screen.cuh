@@ -387,7 +387,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             } else {
                 cp_async_wait_group<1>(); // everything but this refill's positions has landed
             }
-            const bool have = lane < n1;
+            // (a hit outside the caller's reference window -- repeat-masker variant -- is counted, not screened)
+            const bool have = lane < n1 && r_next - H.win_lo <= H.win_hi - H.win_lo;
             uint32_t r0 = 0, rowid = 0, vkey = 0;
             if (have) {
                 const uint32_t meta = ring_meta[(head + lane) & (uint32_t)(SCR_RING - 1)];
@@ -503,7 +504,10 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     }
     if (ext_tiles) atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_EXT_LO), 32ull * ext_tiles);
     if (lane == 0) {
-        if (acc_hits) atomicAdd(counters + CTR_NHITS, acc_hits); // uint32 wrap-around like the reference's scan
+        if (acc_hits) {
+            atomicAdd(counters + CTR_NHITS, acc_hits); // uint32 wrap-around like the reference's scan
+            atomicAdd(reinterpret_cast<unsigned long long *>(counters + CTR_NHITS64), (unsigned long long)acc_hits);
+        }
         if (acc_seeds) atomicAdd(counters + CTR_NSEEDS, acc_seeds);
         if (any_hits) atomicMax(counters + CTR_LASTKEY, acc_last);
         if (acc_walked) atomicAdd(counters + CTR_WALKED, acc_walked);

@@ -144,3 +144,133 @@ k_finalize_small(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_seg
 }
 
 } // namespace sa
+
+// ---------------------------------------------------------------------------------------------
+// Repeat-masker variant (repeat_masker_src/seed_filter.cu:819-835): three stable sorts
+// and two unique passes.  Each of the reference's comparators is extended here to a TOTAL order by
+// appending the order the records had before that stable sort, which is itself a function of the
+// records (never of the hit order):
+//   :819 hspComp      (query_start, len desc, ref_start, score desc)            -- already total
+//   :821 unique_copy(hspEqual)      exact copies (adjacent under a total order)
+//   :825 hspDiagComp  (diagonal, ref_start, query_start, score desc) + ties keep the hspComp order:
+//                     equal q, r, score => they differ in len only => len desc
+//   :827 unique_copy(hspDiagEqual)  same diagonal + containment, against the predecessor of the input
+//   :833 hspFinalComp (query_start, score desc, ref_start desc) + ties keep the order before it: equal
+//                     q, r, score => one diagonal, they differ in len only => len desc
+namespace sa {
+
+struct CompRmFirst {
+    __device__ __forceinline__ bool operator()(const Anchor &x, const Anchor &y) const {
+        if (x.tag != y.tag) return x.tag < y.tag;
+        if (x.query_start != y.query_start) return x.query_start < y.query_start;
+        if (x.len != y.len) return x.len > y.len;
+        if (x.ref_start != y.ref_start) return x.ref_start < y.ref_start;
+        return x.score > y.score;
+    }
+};
+struct CompRmDiag {
+    __device__ __forceinline__ bool operator()(const Anchor &x, const Anchor &y) const {
+        if (x.tag != y.tag) return x.tag < y.tag;
+        const uint32_t dx = x.ref_start - x.query_start, dy = y.ref_start - y.query_start;
+        if (dx != dy) return dx < dy;
+        if (x.ref_start != y.ref_start) return x.ref_start < y.ref_start;
+        if (x.query_start != y.query_start) return x.query_start < y.query_start;
+        if (x.score != y.score) return x.score > y.score;
+        return x.len > y.len;
+    }
+};
+struct CompRmFinal {
+    __device__ __forceinline__ bool operator()(const Anchor &x, const Anchor &y) const {
+        if (x.tag != y.tag) return x.tag < y.tag;
+        if (x.query_start != y.query_start) return x.query_start < y.query_start;
+        if (x.score != y.score) return x.score > y.score;
+        if (x.ref_start != y.ref_start) return x.ref_start > y.ref_start;
+        return x.len > y.len;
+    }
+};
+__device__ __forceinline__ bool rm_exact_equal(const Anchor &x, const Anchor &y) { // hspEqual, :79-84
+    return x.ref_start == y.ref_start && x.query_start == y.query_start && x.len == y.len && x.score == y.score;
+}
+// minus-strand records back to forward coordinates (compress_output, :705-709)
+__device__ __forceinline__ void rm_to_forward(Anchor &a, uint32_t block_len) {
+    a.query_start = block_len - 1u - (a.query_start + a.len);
+}
+
+__global__ void __launch_bounds__(256)
+k_rm_to_forward(Anchor *__restrict__ a, uint32_t n, uint32_t block_len) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) rm_to_forward(a[i], block_len);
+}
+
+// unique_copy(hspEqual) on the sorted input; survivors unordered (the next sort is total)
+__global__ void __launch_bounds__(256)
+k_dedupe_exact(const Anchor *__restrict__ in, uint32_t n, Anchor *__restrict__ out, uint32_t *__restrict__ out_count) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const Anchor cur = in[i];
+        bool keep = true;
+        if (i > 0) {
+            const Anchor prev = in[i - 1];
+            keep = prev.tag != cur.tag || !rm_exact_equal(prev, cur);
+        }
+        if (keep) out[atomicAdd(out_count, 1u)] = cur;
+    }
+}
+
+// one-block version of the whole chain for <= FINALIZE_CAP anchors (same contract as k_finalize_small)
+__global__ void __launch_bounds__(FINALIZE_THREADS)
+k_finalize_small_rm(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_segment *__restrict__ out,
+                    uint32_t *__restrict__ counters, int rev, uint32_t block_len) {
+    __shared__ Anchor a[FINALIZE_CAP];
+    __shared__ Anchor b[FINALIZE_CAP];
+    __shared__ uint32_t kept, kept2;
+    const uint32_t n = counters[0]; // CTR_ANCHORS
+    if (n > FINALIZE_CAP || n > anchor_cap) {
+        if (threadIdx.x == 0) counters[6] = 0xFFFFFFFFu;
+        return;
+    }
+    if (n == 0) {
+        if (threadIdx.x == 0) counters[6] = 0;
+        return;
+    }
+    Anchor pad; // sorts after every real anchor under all three orders
+    pad.tag = 0xFFFFFFFFu; pad.ref_start = 0xFFFFFFFFu; pad.query_start = 0xFFFFFFFFu; pad.len = 0; pad.score = 0;
+    auto pow2 = [](uint32_t v) { int p = 1; while (p < (int)v) p <<= 1; return p; };
+    const int n2 = pow2(n);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        Anchor x = pad;
+        if (i < (int)n) { x = anchors[i]; if (rev) rm_to_forward(x, block_len); }
+        a[i] = x;
+    }
+    if (threadIdx.x == 0) { kept = 0; kept2 = 0; }
+    __syncthreads();
+    block_bitonic_sort(a, n2, CompRmFirst());
+    for (int i = threadIdx.x; i < (int)n; i += blockDim.x) {
+        const bool keep = i == 0 || a[i - 1].tag != a[i].tag || !rm_exact_equal(a[i - 1], a[i]);
+        if (keep) b[atomicAdd(&kept, 1u)] = a[i];
+    }
+    __syncthreads();
+    const uint32_t m = kept;
+    const int m2 = pow2(m);
+    for (int i = (int)m + threadIdx.x; i < m2; i += blockDim.x) b[i] = pad;
+    __syncthreads();
+    block_bitonic_sort(b, m2, CompRmDiag());
+    for (int i = threadIdx.x; i < (int)m; i += blockDim.x) {
+        const bool keep = i == 0 || b[i - 1].tag != b[i].tag || !hsp_equal(b[i - 1], b[i]);
+        if (keep) a[atomicAdd(&kept2, 1u)] = b[i];
+    }
+    __syncthreads();
+    const uint32_t k = kept2;
+    const int k2 = pow2(k);
+    for (int i = (int)k + threadIdx.x; i < k2; i += blockDim.x) a[i] = pad;
+    __syncthreads();
+    block_bitonic_sort(a, k2, CompRmFinal());
+    for (int i = threadIdx.x; i < (int)k; i += blockDim.x) {
+        sa_segment s;
+        s.ref_start = a[i].ref_start; s.query_start = a[i].query_start; s.len = a[i].len; s.score = a[i].score;
+        out[i] = s;
+    }
+    if (threadIdx.x == 0) counters[6] = k;
+}
+
+} // namespace sa

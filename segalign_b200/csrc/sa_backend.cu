@@ -149,6 +149,8 @@ struct Global {
     bool use_fused = true;     // SEGALIGN_B200_FUSED=0 always takes the general (materialised hit list) path
     int filter2_grid = 0;      // tile-walk kernel (k_filter_hits2)
     int filter3_grid = 0;      // popcount screen + tile walk (k_filter_hits3), the default on the fused path
+    int filter3_grid_alone = 0; // the same when no other call is in flight: every block slot of every SM
+    std::atomic<int> calls_in_flight[64] = {}; // per GPU of the pool
     int filter_kernel = 3;     // SEGALIGN_B200_FILTER_KERNEL=2 selects the tile-walk-only kernel on the fused path
     ScreenConsts screen = {};  // class scores of the popcount screen (screen_bound.h)
     int extend_grid = 0;
@@ -158,6 +160,8 @@ struct Global {
     bool use_compact = true;   // SEGALIGN_B200_COMPACT_SEEDS=0: always copy seed vectors as they are
     uint32_t ref_len = 0;
     bool ref_loaded = false, table_ready = false;
+    bool ascii_holds_ref = false; // the per-GPU ASCII staging buffers still hold the reference block (sa_rm_send_query)
+    bool rm_query = false;        // query slot 0 = the reference block itself + its reverse complement (repeat-masker variant)
     uint32_t query_len[SA_BUFFER_DEPTH] = {};
     bool query_loaded[SA_BUFFER_DEPTH] = {};
     ShapeDesc shape = {};
@@ -377,6 +381,15 @@ struct PhaseTimer {
     }
 };
 
+template <typename Comp>
+int sort_anchors_by(Workspace *w, Anchor *keys, uint32_t n, Comp comp) {
+    size_t bytes = 0;
+    CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, comp, w->stream), SA_ERR_KERNEL);
+    TRY(ensure(w->d_temp, w->temp_cap, bytes, "sort_temp"));
+    CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, comp, w->stream), SA_ERR_KERNEL);
+    return SA_OK;
+}
+
 int sort_anchors(Workspace *w, Anchor *keys, uint32_t n, bool lastz) {
     size_t bytes = 0;
     if (lastz) CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, CompLastz(), w->stream), SA_ERR_KERNEL);
@@ -393,6 +406,10 @@ struct CallInput {
     uint32_t max_items;  // seed words (SRC_SEEDS) or positions x words per position (SRC_RANGE)
     uint32_t q_start, q_end, per; // SRC_RANGE
     int transition;
+    // repeat-masker variant (repeat_masker_src/seed_filter.cu:724): the block against itself / its reverse
+    // complement, hits outside [win_lo, win_hi] counted but not extended, its own sort/unique chain and header
+    bool rm = false;
+    uint32_t win_lo = 0, win_hi = 0xFFFFFFFFu;
 };
 
 // SRC_RANGE, general path only: seed words of src/seeder.cpp:57-74 on the device; their count
@@ -454,9 +471,12 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
                  uint32_t *out_count, uint32_t *out_num_seeds, PhaseTimer &pt) {
     GpuCtx &g = G.gpus[w->gpu];
     cudaStream_t st = w->stream;
+    struct InFlight { std::atomic<int> &c;
+                      explicit InFlight(std::atomic<int> &c_) : c(c_) { c.fetch_add(1, std::memory_order_relaxed); }
+                      ~InFlight() { c.fetch_sub(1, std::memory_order_relaxed); } } in_flight(G.calls_in_flight[w->gpu & 63]);
     uint64_t launches = 0;
     uint32_t num_hits = 0, num_iter = 0, num_seeds = 0, n_pre = 0, n_final = 0, n_surv = 0, n_walked = 0;
-    unsigned long long ext_cells = 0;
+    unsigned long long ext_cells = 0, num_hits64 = 0;
     const SeqPlanes &q = rev ? g.q_rc[buffer] : g.q_fwd[buffer];
     const bool filter = G.filter_ok && G.use_filter;
     bool fused = filter && G.use_fused;
@@ -475,6 +495,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.diag_all_positive = G.diag_all_positive;
     P.scores_fit_int8 = G.filter_ok;
     P.soft_runs = (((G.term_codes >> L_NT) & 1u) == 0 || ((G.term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
+    P.win_lo = in.win_lo; P.win_hi = in.win_hi;
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
     F.rp2 = g.ref.p2; F.rsoft = g.ref.softmap; F.ref_has_soft = g.ref.has_soft ? 1 : 0;
@@ -485,6 +506,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     H.num_items = max_items;
     H.index_table = g.d_index; H.pos_table = g.d_pos; H.seed_size = G.seed_size;
     H.index_size = g.index_size; H.query_len = q.len;
+    H.win_lo = in.win_lo; H.win_hi = in.win_hi;
     const SeedBounds SB = {g.index_size, q.len, G.seed_size};
     H.j0 = in.q_start; H.per = in.per; H.shape = G.shape;
     DedupTable D;
@@ -515,10 +537,13 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             if (G.filter_kernel == 3 && G.screen.enabled) {
                 FilterParams F3 = F;
                 F3.k_mul = SCR_K_MUL;
+                // a launch normally leaves one block slot per SM to the next call's kernel (their head and tail
+                // overlap); a call that is alone on the device takes them all
+                const int grid3 = G.calls_in_flight[w->gpu & 63].load(std::memory_order_relaxed) <= 1 ? G.filter3_grid_alone : G.filter3_grid;
                 if (in.src == SRC_SEEDS)
-                    k_filter_hits3<SRC_SEEDS><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_SEEDS><<<grid3, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
                 else
-                    k_filter_hits3<SRC_RANGE><<<G.filter3_grid, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
+                    k_filter_hits3<SRC_RANGE><<<grid3, SCR_THREADS, SCR_SMEM_BYTES, st>>>(F3, G.screen, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
             } else {
                 if (in.src == SRC_SEEDS)
                     k_filter_hits2<SRC_SEEDS><<<G.filter2_grid, FILTER_THREADS, lut_bytes, st>>>(F, H, g.d_sub_mat, w->d_surv, surv_cap, w->d_counters);
@@ -540,7 +565,8 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             CU(cub::DeviceScan::InclusiveSum(nullptr, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
             TRY(ensure(w->d_temp, w->temp_cap, bytes, "scan_temp"));
             // 1. bucket sizes + inclusive scan (seed_filter.cu:712-714)
-            k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, SB, w->d_prefix);
+            k_count_hits<<<grid_for(max_items, 256), 256, 0, st>>>(w->d_seeds, max_items, w->d_plan + 2, g.d_index, SB, w->d_prefix,
+                                                                        reinterpret_cast<unsigned long long *>(w->d_counters + CTR_NHITS64));
             CU(cub::DeviceScan::InclusiveSum(w->d_temp, bytes, w->d_prefix, w->d_prefix, (int)max_items, st), SA_ERR_KERNEL);
             // 2. iteration plan on the device (seed_filter.cu:718-745)
             k_plan_iterations<<<1, 32, 0, st>>>(w->d_prefix, max_items, G.max_hits, (uint32_t)std::min(w->limit_cap, w->bound_cap),
@@ -582,7 +608,8 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         pt.mark(PH_EXTEND);
         // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the anchors
         //    fit; the counters, the plan and the first FINALIZE_CAP records come back together
-        k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters);
+        if (in.rm) k_finalize_small_rm<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters, rev, g.ref.len);
+        else k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters);
         pt.mark(PH_SORT);
         launches += 2;
         CU(cudaMemcpyAsync(w->h_small, w->d_counters, CTR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
@@ -591,6 +618,10 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
         n_pre = w->h_small[CTR_ANCHORS];
         memcpy(&ext_cells, &w->h_small[CTR_EXT_LO], 8);
+        memcpy(&num_hits64, &w->h_small[CTR_NHITS64], 8);
+        if (in.rm && num_hits64 > 0xFFFFFFFFull)
+            return fail(SA_ERR_STATE, "repeat-masker call with %llu seed hits: more than 2^32 hits per call are not supported",
+                        (unsigned long long)num_hits64);
         if (fused) {
             num_hits = w->h_small[CTR_NHITS];
             num_seeds = w->h_small[CTR_NSEEDS];
@@ -636,6 +667,30 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         if (w->h_small[CTR_OUT] != 0xFFFFFFFFu) {
             n_final = w->h_small[CTR_OUT];
             staged = true;
+        } else if (in.rm) {
+            // repeat_masker_src/seed_filter.cu:819-835 device-wide (kernels_sort.cuh: the three total orders)
+            auto count_of = [&](uint32_t &n) -> int {
+                CU(cudaMemcpyAsync(w->h_small, w->d_counters + CTR_DEDUPE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
+                CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
+                n = w->h_small[0];
+                return SA_OK;
+            };
+            if (rev) k_rm_to_forward<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, g.ref.len);
+            TRY(sort_anchors_by(w, w->d_anchors_a, n_pre, CompRmFirst()));
+            TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
+            CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+            k_dedupe_exact<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + CTR_DEDUPE);
+            uint32_t n1 = 0;
+            TRY(count_of(n1));
+            TRY(sort_anchors_by(w, w->d_anchors_b, n1, CompRmDiag()));
+            CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
+            k_dedupe<<<grid_for(n1, 256), 256, 0, st>>>(w->d_anchors_b, n1, w->d_anchors_a, w->d_counters + CTR_DEDUPE);
+            TRY(count_of(n_final));
+            TRY(sort_anchors_by(w, w->d_anchors_a, n_final, CompRmFinal()));
+            TRY(ensure(w->d_out, w->out_cap, n_final, "hsp_out"));
+            k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_a, n_final, w->d_out);
+            launches += 14;
+            pt.mark(PH_SORT);
         } else {
             // many distinct anchors (repeat families, forced small iterations): device-wide sorts
             TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
@@ -666,10 +721,17 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
                         (unsigned long)n_final * sizeof(sa_segment), cudaGetErrorString(e));
         }
     }
-    res[0].ref_start = 0;
-    res[0].query_start = 0;
-    res[0].len = n_final;
-    res[0].score = (int32_t)num_hits;
+    if (in.rm) { // repeat_masker_src/seed_filter.cu:856-861: 64-bit totals, low word first
+        res[0].ref_start = (uint32_t)(num_hits64 & 0xFFFFFFFFull);
+        res[0].query_start = (uint32_t)(num_hits64 >> 32);
+        res[0].len = n_final;
+        res[0].score = 0;
+    } else {
+        res[0].ref_start = 0;
+        res[0].query_start = 0;
+        res[0].len = n_final;
+        res[0].score = (int32_t)num_hits;
+    }
     pt.mark(PH_D2H);
     if (pt.on) CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
@@ -813,8 +875,9 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         // Two of the three block slots per SM by default: the third is left to the next call's kernel
         // (another stream), whose head overlaps this one's tail -- 8 % more calls per second with 16
         // callers than three blocks per SM, at 6 % more time for a launch that runs alone.
+        G.filter3_grid_alone = std::max(1, per_sm3) * std::max(1, sms);
         per_sm3 = std::min(per_sm3, 2);
-        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) per_sm3 = atoi(e);
+        if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) { per_sm3 = atoi(e); G.filter3_grid_alone = per_sm3 * std::max(1, sms); }
         G.filter3_grid = std::max(1, per_sm3) * std::max(1, sms);
         G.filter_kernel = 3;
         if (const char *e = getenv("SEGALIGN_B200_FILTER_KERNEL")) { int v = atoi(e); if (v == 2 || v == 3) G.filter_kernel = v; }
@@ -887,6 +950,7 @@ int sa_send_ref(const char *seq, size_t start_addr, uint32_t len) {
     G.ref_len = len;
     const auto t0 = std::chrono::steady_clock::now();
     TRY(upload_block_all_gpus(seq + start_addr, len, -1, "ref_seq"));
+    G.ascii_holds_ref = true;
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     {
         std::lock_guard<std::mutex> l(G.stats_mu);
@@ -1004,6 +1068,7 @@ int sa_clear_ref(void) {
         g.index_size = g.num_pos = 0;
     }
     G.ref_loaded = G.table_ready = false;
+    G.ascii_holds_ref = false;
     return SA_OK;
 }
 
@@ -1014,6 +1079,7 @@ int sa_send_query(const char *query_base, size_t start_addr, uint32_t len, uint3
     if (!query_base && len) return fail(SA_ERR_ARG, "query_base is NULL");
     G.query_len[buffer] = len;
     const auto t0 = std::chrono::steady_clock::now();
+    G.ascii_holds_ref = false;
     TRY(upload_block_all_gpus(query_base + start_addr, len, (int)buffer, "query_seq"));
     const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     {
@@ -1033,6 +1099,7 @@ int sa_clear_query(uint32_t buffer) {
         TRY(free_planes(g.q_rc[buffer], g.ctrl));
     }
     G.query_loaded[buffer] = false;
+    if (buffer == 0) G.rm_query = false;
     return SA_OK;
 }
 
@@ -1137,6 +1204,102 @@ int sa_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, i
     return run_pipeline(w, in, rev, buffer, out, out_count, out_num_seeds, pt);
 }
 
+// ---------------------------------------------------------------- repeat-masker variant
+// repeat_masker_src/seed_filter.cu:951-961 SendQueryWriteRequest(): the "query" is the resident block itself
+// (plus strand) and its reverse complement, built on the device (minus strand).  Here both come out of one
+// more encode pass over the block's ASCII bytes, which are still in the per-GPU staging buffers.
+int sa_rm_send_query(void) {
+    if (!G.ref_loaded) return fail(SA_ERR_STATE, "SendRefWriteRequest must precede the repeat masker's SendQueryWriteRequest");
+    if (!G.ascii_holds_ref) return fail(SA_ERR_STATE, "the reference block's bytes are no longer staged: call right after SendRefWriteRequest");
+    if (G.query_loaded[0]) return fail(SA_ERR_STATE, "ClearQuery must precede a second SendQueryWriteRequest");
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        TRY(enqueue_encode(g, G.ref_len, g.q_fwd[0], &g.q_rc[0], "seq_rc"));
+    }
+    for (auto &g : G.gpus) {
+        CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
+        CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+    }
+    G.query_len[0] = G.ref_len;
+    G.query_loaded[0] = true;
+    G.rm_query = true;
+    return SA_OK;
+}
+int sa_rm_clear_query(void) { return sa_clear_query(0); }
+
+static int rm_check(uint32_t ref_start, uint32_t ref_end) {
+    TRY(check_call_state(0));
+    if (!G.rm_query) return fail(SA_ERR_STATE, "query slot 0 does not hold the block's own reverse complement (sa_rm_send_query)");
+    if (ref_end < ref_start) return fail(SA_ERR_ARG, "ref_end < ref_start");
+    return SA_OK;
+}
+
+int sa_rm_seed_and_filter(const uint64_t *seeds, uint32_t num_seeds, int rev, uint32_t ref_start, uint32_t ref_end,
+                          sa_segment **out, uint32_t *out_count) {
+    if (!out || !out_count) return fail(SA_ERR_ARG, "out/out_count is NULL");
+    TRY(rm_check(ref_start, ref_end));
+    if (num_seeds > G.max_seeds) { // repeat_masker_src/seed_filter.cu:730-734
+        printf("MAX_SEEDS exceeded\n");
+        return fail(SA_ERR_MAX_SEEDS, "num_seeds %u > MAX_SEEDS %u", num_seeds, G.max_seeds);
+    }
+    if (num_seeds == 0) {
+        sa_segment *res = (sa_segment *)calloc(1, sizeof(sa_segment));
+        *out = res; *out_count = 1;
+        return SA_OK;
+    }
+    if (!seeds) return fail(SA_ERR_ARG, "seeds is NULL");
+    Workspace *w = acquire_ws();
+    WsGuard guard(w);
+    CU(cudaSetDevice(G.gpus[w->gpu].device), SA_ERR_SET_DEVICE);
+    PhaseTimer pt(w);
+    pt.mark(PH_START);
+    TRY(ensure(w->d_seeds, w->seeds_cap, num_seeds, "seed_offsets"));
+    TRY(ensure(w->d_prefix, w->prefix_cap, num_seeds, "hit_num"));
+    CU(cudaMemcpyAsync(w->d_seeds, seeds, (size_t)num_seeds * sizeof(uint64_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    {
+        std::lock_guard<std::mutex> l(G.stats_mu);
+        G.stats.h2d_bytes += (uint64_t)num_seeds * sizeof(uint64_t);
+    }
+    w->h_small[20] = num_seeds;
+    CU(cudaMemcpyAsync(w->d_plan + 2, w->h_small + 20, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream), SA_ERR_MEMCPY);
+    pt.mark(PH_SEEDS);
+    CallInput in = {};
+    in.src = SRC_SEEDS; in.max_items = num_seeds; in.per = 1; in.transition = G.transition;
+    in.rm = true; in.win_lo = ref_start; in.win_hi = ref_end;
+    return run_pipeline(w, in, rev, 0, out, out_count, nullptr, pt);
+}
+
+int sa_rm_seed_and_filter_range(uint32_t q_start, uint32_t q_end, int transition, int rev, uint32_t ref_start,
+                                uint32_t ref_end, sa_segment **out, uint32_t *out_count, uint32_t *out_num_seeds) {
+    if (!out || !out_count) return fail(SA_ERR_ARG, "out/out_count is NULL");
+    TRY(rm_check(ref_start, ref_end));
+    if (q_end < q_start) return fail(SA_ERR_ARG, "q_end < q_start");
+    if (q_end > G.ref_len) return fail(SA_ERR_ARG, "range [%u,%u) exceeds the block (%u)", q_start, q_end, G.ref_len);
+    const uint32_t n = q_end - q_start;
+    const uint32_t per = 1u + (transition ? (uint32_t)G.shape.num_trans : 0u);
+    if (n == 0) {
+        if (out_num_seeds) *out_num_seeds = 0;
+        sa_segment *res = (sa_segment *)calloc(1, sizeof(sa_segment));
+        *out = res; *out_count = 1;
+        return SA_OK;
+    }
+    if ((uint64_t)n * per > G.max_seeds) {
+        printf("MAX_SEEDS exceeded\n");
+        return fail(SA_ERR_MAX_SEEDS, "range of %u positions x %u words > MAX_SEEDS %u", n, per, G.max_seeds);
+    }
+    Workspace *w = acquire_ws();
+    WsGuard guard(w);
+    CU(cudaSetDevice(G.gpus[w->gpu].device), SA_ERR_SET_DEVICE);
+    PhaseTimer pt(w);
+    pt.mark(PH_START);
+    CallInput in = {};
+    in.src = SRC_RANGE; in.max_items = n * per;
+    in.q_start = q_start; in.q_end = q_end; in.per = per; in.transition = transition;
+    in.rm = true; in.win_lo = ref_start; in.win_hi = ref_end;
+    pt.mark(PH_SEEDS);
+    return run_pipeline(w, in, rev, 0, out, out_count, out_num_seeds, pt);
+}
+
 void sa_release_result(sa_segment *out) { free(out); }
 
 int sa_shutdown_processor(void) {
@@ -1161,6 +1324,7 @@ int sa_shutdown_processor(void) {
     }
     G.gpus.clear();
     G.interface_ready = G.processor_ready = G.ref_loaded = G.table_ready = false;
+    G.ascii_holds_ref = G.rm_query = false;
     for (int b = 0; b < SA_BUFFER_DEPTH; b++) G.query_loaded[b] = false;
     return SA_OK;
 }

@@ -71,6 +71,7 @@ struct ExtendParams {
     int diag_all_positive; // sub_mat[c][c] > 0 for c in ACGT: enables the all-match tile path
     int scores_fit_int8;   // ACGT x ACGT block within [-128,127]: enables the dp4a group path
     int soft_runs;         // lower case or N are NOT terminators under this matrix: walks pass through their runs
+    uint32_t win_lo, win_hi; // repeat-masker variant: reference window of the call (0 .. 0xFFFFFFFF otherwise)
 };
 
 struct Anchor { // HSP + the reference iteration it belongs to (dedupe scope)

@@ -16,6 +16,11 @@
 // The mirror declarations below keep this file compilable without the reference tree; they
 // must stay layout-identical to src/graph.h:25-30 (segmentPair) and common/DRAM.h:4-12 (DRAM).
 // Compile with the same libstdc++ ABI as the host code (std::vector crosses the boundary).
+//
+// -DSA_SHIM_REPEAT_MASKER builds the flavour segalign_repeat_masker links: the three
+// symbols whose signatures differ there (repeat_masker_src/seed_filter.h:5-14) --
+// g_SendQueryWriteRequest(), g_SeedAndFilter(seeds, rev, ref_start, ref_end), g_ClearQuery() -- and no
+// query_DRAM import (the block is aligned against itself).
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +46,9 @@ public:
     ~DRAM();
 };
 
+#ifndef SA_SHIM_REPEAT_MASKER
 extern DRAM *query_DRAM;        // src/store.h:7, defined by the host (main.cpp:30)
+#endif
 extern int shape_pos[32];       // common/ntcoding.cpp:6
 extern int shape_size;          // common/ntcoding.cpp:7 (number of care positions)
 extern int transition_pos[32];  // common/ntcoding.cpp:8
@@ -53,10 +60,17 @@ typedef void (*ShutdownProcessor_ptr)();
 typedef void (*InitializeProcessor_ptr)(bool transition, uint32_t WGA_CHUNK, uint32_t input_seed_size,
                                         int *sub_mat, int input_xdrop, int input_hspthresh,
                                         bool input_noentropy);
+#ifndef SA_SHIM_REPEAT_MASKER
 typedef void (*SendQueryWriteRequest_ptr)(size_t addr, uint32_t len, uint32_t buffer);
 typedef std::vector<segmentPair> (*SeedAndFilter_ptr)(std::vector<uint64_t> seed_offset_vector,
                                                       bool rev, uint32_t buffer);
 typedef void (*ClearQuery_ptr)(uint32_t buffer);
+#else // repeat_masker_src/seed_filter.h:5-8
+typedef void (*SendQueryWriteRequest_ptr)();
+typedef std::vector<segmentPair> (*SeedAndFilter_ptr)(std::vector<uint64_t> seed_offset_vector, bool rev,
+                                                      uint32_t ref_start, uint32_t ref_end);
+typedef void (*ClearQuery_ptr)();
+#endif
 
 namespace {
 
@@ -94,19 +108,31 @@ void InitializeProcessor(bool transition, uint32_t WGA_CHUNK, uint32_t input_see
 
 void SendRefWriteRequest(char *seq, size_t addr, uint32_t len) { check(sa_send_ref(seq, addr, len)); }
 void ClearRef() { check(sa_clear_ref()); }
+void ShutdownProcessor() { check(sa_shutdown_processor()); }
+#ifndef SA_SHIM_REPEAT_MASKER
 void SendQueryWriteRequest(size_t addr, uint32_t len, uint32_t buffer) {
     check(sa_send_query(query_DRAM->buffer, addr, len, buffer)); // seed_filter.cu:910
 }
 void ClearQuery(uint32_t buffer) { check(sa_clear_query(buffer)); }
-void ShutdownProcessor() { check(sa_shutdown_processor()); }
 
 std::vector<segmentPair> SeedAndFilter(std::vector<uint64_t> seed_offset_vector, bool rev, uint32_t buffer) {
     sa_segment *out = nullptr;
     uint32_t n = 0;
     check(sa_seed_and_filter(seed_offset_vector.data(), (uint32_t)seed_offset_vector.size(), rev, buffer,
                              &out, &n));
+#else
+void SendQueryWriteRequest() { check(sa_rm_send_query()); }   // repeat_masker_src/seed_filter.cu:951-961
+void ClearQuery() { check(sa_rm_clear_query()); }             // :963-971
+
+std::vector<segmentPair> SeedAndFilter(std::vector<uint64_t> seed_offset_vector, bool rev, uint32_t ref_start,
+                                       uint32_t ref_end) {                                   // :724
+    sa_segment *out = nullptr;
+    uint32_t n = 0;
+    check(sa_rm_seed_and_filter(seed_offset_vector.data(), (uint32_t)seed_offset_vector.size(), rev, ref_start,
+                                ref_end, &out, &n));
+#endif
     const segmentPair *p = reinterpret_cast<const segmentPair *>(out);
-    std::vector<segmentPair> result(p, p + n); // element 0 = header {0,0,len=#HSPs,score=#hits}
+    std::vector<segmentPair> result(p, p + n); // element 0 = header (hit and anchor totals)
     sa_release_result(out);
     return result;
 }

@@ -409,3 +409,205 @@ def run_reference_printer(workdir: Path, r_table, q_table, rc_table, block, inte
             f.write(struct.pack("<I", h.size) + h.tobytes())
     p = subprocess.run([str(SEGPRINT_RUNNER), str(inp), str(out_dir)], check=True, capture_output=True, text=True)
     return {q.name: q.read_text() for q in out_dir.glob("*.segments")}, p.stdout.splitlines()
+
+
+# ------------------------------------------------------------------------------ repeat-masker variant
+RM_ORACLE_RUNNER = ROOT / "oracle" / "_ref" / "rm_oracle_runner"
+RM_NEW_RUNNER = ROOT / "oracle" / "_ref" / "rm_new_runner"
+RM_GOLDEN_DIR = GOLDEN_DIR / "rm"
+
+# The repeat masker aligns ONE sequence against itself: a case's reference is the sequence, its query
+# is ignored.  neigh_prop = --neighbor_proportion (repeat_masker_src/main.cpp:50): which part of the
+# sequence around a query interval its hits may come from.
+RM_CASES = [
+    (Case("rm_repeats", "repeats", dict(n=36_000, copies=40, low_complexity=10), lastz_interval=12_000, wga_chunk=5_000), 0.4),
+    (Case("rm_repeats_whole", "repeats", dict(n=30_000, copies=30, low_complexity=8), rng_seed=31, wga_chunk=11_000), 1.0),
+    (Case("rm_masked_multichrom", "masked_multichrom", dict(n=40_000, n_len=200), rng_seed=32, lastz_interval=9_000,
+          wga_chunk=4_000), 0.5),
+    (Case("rm_multi_iter", "repeats", dict(n=28_000, copies=25, low_complexity=6), rng_seed=33, lastz_interval=15_000,
+          wga_chunk=6_000, max_hits_override=900), 0.6),
+    (Case("rm_plus_only_noentropy", "repeats", dict(n=26_000, copies=24, low_complexity=12), rng_seed=34, strand="plus",
+          noentropy=True, lastz_interval=8_000), 0.3),
+    (Case("rm_iupac_notransition", "shared_ambiguous", dict(n=30_000, runs=20), rng_seed=35, transition=False, strand="plus",
+          ambiguous="iupac", hspthresh=2200, lastz_interval=10_000, wga_chunk=4_000), 0.7),
+]
+RM_CASES_BY_NAME = {c.name: (c, p) for c, p in RM_CASES}
+
+
+def rm_intervals(seq_len: int, seed_size: int, interval: int, neigh_prop: float):
+    """repeat_masker_src/main.cpp:323-420 for one block holding the whole sequence:
+    [(start, end, ref_start, ref_end)]."""
+    import math
+    f32 = np.float32
+    total = int(math.ceil(f32(seq_len) / f32(interval)))
+    num_neigh = int(math.ceil(f32(f32(neigh_prop) * f32(total))))
+    left_n = int(math.ceil(f32(num_neigh - 1) / f32(2)))
+    right_n = num_neigh - 1 - left_n
+    left_ov, right_ov = left_n * interval, right_n * interval
+    max_len = left_ov + interval + right_ov
+    out, start, end_pos = [], 0, seq_len - seed_size
+    while start < end_pos:
+        end = min(end_pos, start + interval)
+        left_limit, right_limit = start < left_ov, end + right_ov > seq_len
+        if left_limit:
+            rs, re_ = 0, (seq_len if right_limit else min(seq_len, max_len))
+        elif right_limit:
+            rs, re_ = (0 if seq_len < max_len else seq_len - max_len), seq_len
+        else:
+            rs, re_ = start - left_ov, end + right_ov
+        out.append((start, end, rs, re_))
+        start += interval
+    return out
+
+
+def rm_calls(case: Case, seq_len: int, seed_size: int, neigh_prop: float):
+    """Every SeedAndFilter call of the repeat masker's seeder (repeat_masker_src/seeder.cpp:69-150) in
+    order: [(rev, j0, j1, ref_start, ref_end)]."""
+    calls = []
+    for (s, e, rs, re_) in rm_intervals(seq_len, seed_size, case.lastz_interval, neigh_prop):
+        end_pos_rc = seq_len - 1 - s
+        for i in range(s, e, case.wga_chunk):
+            j0, j1 = i, min(i + case.wga_chunk, e)
+            if case.strand in ("plus", "both"):
+                calls.append((0, j0, j1, rs, re_))
+            if case.strand in ("minus", "both"):
+                r0 = seq_len - 1 - j1
+                calls.append((1, r0, min(r0 + case.wga_chunk, end_pos_rc), rs, re_))
+    return calls
+
+
+@dataclass
+class RmDump:
+    calls: list           # [(rev, j0, j1, num_seeds, ref_start, ref_end, header(4 x u32), segs)]
+    times: np.ndarray     # upload, table, seed_and_filter (s)
+    counters: np.ndarray  # seeds, hits, hsps, device MAX_HITS
+
+
+def read_rm_dump(path: Path) -> RmDump:
+    """SARMO001, written by oracle/rm_driver.cpp."""
+    b = Path(path).read_bytes()
+    assert b[:8] == b"SARMO001", "bad dump magic"
+    off = 8
+    (ncalls,) = struct.unpack_from("<I", b, off); off += 4
+    calls = []
+    for _ in range(ncalls):
+        rev, cs, ce, ns, rs, re_, nseg, h0, h1, h2, h3 = struct.unpack_from("<11I", b, off); off += 44
+        segs = np.frombuffer(b, dtype=SEGMENT_DTYPE, count=nseg, offset=off).copy(); off += 16 * nseg
+        calls.append((rev, cs, ce, ns, rs, re_, (h0, h1, h2, h3), segs))
+    times = np.frombuffer(b, dtype="<f8", count=3, offset=off).copy(); off += 24
+    counters = np.frombuffer(b, dtype="<u8", count=4, offset=off).copy()
+    return RmDump(calls, times, counters)
+
+
+def run_rm_runner(binary: Path, case: Case, neigh_prop: float, workdir: Path) -> RmDump:
+    workdir.mkdir(parents=True, exist_ok=True)
+    cf, of = workdir / f"{case.name}.case", workdir / f"{case.name}.{binary.name}.out"
+    ref, _ = case.inputs()
+    write_case_file(case, cf, ref, ref[:1])
+    subprocess.run([str(binary), str(cf), str(of), "--neigh-prop", repr(float(neigh_prop))], check=True, stderr=subprocess.PIPE)
+    return read_rm_dump(of)
+
+
+def rm_golden_path(case: Case) -> Path:
+    return RM_GOLDEN_DIR / f"{case.name}.npz"
+
+
+def save_rm_golden(case: Case, dump: RmDump, seq) -> None:
+    hdr = np.array([(c[0], c[1], c[2], c[3], c[4], c[5], *c[6], c[7].size) for c in dump.calls], dtype=np.uint32).reshape(-1, 11)
+    segs = np.concatenate([c[7] for c in dump.calls]) if dump.calls else np.empty(0, SEGMENT_DTYPE)
+    RM_GOLDEN_DIR.mkdir(exist_ok=True)
+    np.savez_compressed(rm_golden_path(case), hdr=hdr, segs=segs.view(np.uint32).reshape(-1, 4),
+                        digest=np.array(inputs_digest(seq, seq[:0])), max_hits_device=dump.counters[3])
+
+
+def load_rm_golden(case: Case):
+    """-> ([(rev, j0, j1, num_seeds, ref_start, ref_end, segs_with_header)], digest)"""
+    z = np.load(rm_golden_path(case))
+    segs = np.ascontiguousarray(z["segs"]).view(SEGMENT_DTYPE).reshape(-1)
+    calls, off = [], 0
+    for rev, cs, ce, ns, rs, re_, h0, h1, h2, h3, nseg in z["hdr"]:
+        res = np.zeros(int(nseg) + 1, dtype=SEGMENT_DTYPE)
+        res[0] = (h0, h1, h2, np.uint32(h3).view(np.int32))
+        res[1:] = segs[off:off + int(nseg)]
+        off += int(nseg)
+        calls.append((int(rev), int(cs), int(ce), int(ns), int(rs), int(re_), res))
+    return calls, str(z["digest"])
+
+
+def run_rm_cpu_oracle(case: Case, neigh_prop: float, seq=None, max_hits_device: int = 0xFFFFFFFF):
+    """The whole case through oracle/sa_oracle.c's repeat-masker restatement; same layout as load_rm_golden."""
+    from oracle import sa_oracle_py as sao
+    if seq is None:
+        seq, _ = case.inputs()
+    shape = sao.Shape(case.seed_shape)
+    table = sao.Table(shape, seq, seq.size, case.step)
+    enc = sao.encode(seq)
+    enc_rc = sao.rm_revcomp_codes(enc)
+    rc_ascii = sao.revcomp_ascii(seq)     # host RevComp: what the seeder reads minus-strand seeds from
+    mh = case.max_hits_override if case.max_hits_override > 0 else max_hits_device
+    params = sao.make_params(matrix_for(case), case.xdrop, case.hspthresh, case.noentropy, shape.span, mh)
+    out = []
+    for rev, j0, j1, rs, re_ in rm_calls(case, seq.size, shape.span, neigh_prop):
+        seeds = shape.chunk_seeds(rc_ascii if rev else seq, j0, j1, case.transition)
+        if seeds.size == 0:
+            continue
+        res = sao.rm_seed_and_filter(params, table, enc, enc_rc, seeds, bool(rev), rs, re_)
+        out.append((rev, j0, j1, seeds.size, rs, re_, res))
+    return out
+
+
+def assert_rm_calls_equal(got, want, what: str):
+    assert len(got) == len(want), f"{what}: {len(got)} calls vs {len(want)}"
+    for g, w in zip(got, want):
+        assert tuple(g[:6]) == tuple(w[:6]), f"{what}: call key {g[:6]} vs {w[:6]}"
+        gs, ws = g[6], w[6]
+        assert gs[0] == ws[0], f"{what}: header of call {g[:3]}: {gs[0]} vs {ws[0]}"
+        assert gs.size == ws.size, f"{what}: call {g[:3]}: {gs.size - 1} HSPs vs {ws.size - 1}"
+        if not np.array_equal(gs[1:], ws[1:]):
+            bad = np.flatnonzero(gs[1:] != ws[1:])[:5]
+            raise AssertionError(f"{what}: call {g[:3]} differs at {bad}: {gs[1:][bad]} vs {ws[1:][bad]}")
+
+
+def setup_rm_backend(be, case: Case, seq):
+    """repeat_masker_src/main.cpp:256-257, :498-505: InitializeProcessor, SendRefWriteRequest,
+    SendQueryWriteRequest(), GenerateSeedPosTable."""
+    from segalign_b200.backend import shape_pattern
+    be.GenerateShapePos(case.seed_shape)
+    span = len(shape_pattern(case.seed_shape))
+    be.InitializeProcessor(case.transition, case.wga_chunk, span, matrix_for(case), case.xdrop, case.hspthresh,
+                           case.noentropy)
+    if case.max_hits_override > 0:
+        be.set_max_hits(case.max_hits_override)
+    be.SendRefWriteRequest(seq, 0, seq.size)
+    be.RmSendQueryWriteRequest()
+    be.GenerateSeedPosTable(seq, 0, seq.size, case.step)
+    return span
+
+
+def run_rm_backend(be, case: Case, neigh_prop: float, seq=None, device_seeding: bool = False):
+    """The whole repeat-masker case through the CUDA backend (C ABI); layout of load_rm_golden."""
+    from segalign_b200.backend import shape_pattern
+    if seq is None:
+        seq, _ = case.inputs()
+    span = setup_rm_backend(be, case, seq)
+    pattern = shape_pattern(case.seed_shape)
+    rc_ascii = genome.revcomp_ascii(seq)
+    out = []
+    try:
+        for rev, j0, j1, rs, re_ in rm_calls(case, seq.size, span, neigh_prop):
+            if device_seeding:
+                res, ns = be.RmSeedAndFilterRange(j0, j1, case.transition, bool(rev), rs, re_)
+                if ns == 0:
+                    continue
+            else:
+                seeds = genome.chunk_seeds(rc_ascii if rev else seq, j0, j1, pattern, case.transition)
+                if seeds.size == 0:
+                    continue
+                ns = seeds.size
+                res = be.RmSeedAndFilter(seeds, bool(rev), rs, re_)
+            out.append((rev, j0, j1, ns, rs, re_, res))
+    finally:
+        be.RmClearQuery()
+        be.ClearRef()
+        be.ShutdownProcessor()
+    return out
