@@ -101,12 +101,12 @@ __device__ __forceinline__ void block_bitonic_sort(Anchor *a, int n_pow2, Comp l
 
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 k_finalize_small(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_segment *__restrict__ out,
-                 uint32_t *__restrict__ counters) {
+                 uint32_t *__restrict__ counters, uint32_t small_cap) {
     __shared__ Anchor a[FINALIZE_CAP];
     __shared__ Anchor b[FINALIZE_CAP];
     __shared__ uint32_t kept;
     const uint32_t n = counters[0]; // CTR_ANCHORS
-    if (n > FINALIZE_CAP || n > anchor_cap) { // too many for one block (or the append overflowed): host takes the cub path
+    if (n > small_cap || n > anchor_cap) { // too many for one block (or the append overflowed): host takes the cub path
         if (threadIdx.x == 0) counters[6] = 0xFFFFFFFFu;
         return;
     }
@@ -220,12 +220,12 @@ k_dedupe_exact(const Anchor *__restrict__ in, uint32_t n, Anchor *__restrict__ o
 // one-block version of the whole chain for <= FINALIZE_CAP anchors (same contract as k_finalize_small)
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 k_finalize_small_rm(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_segment *__restrict__ out,
-                    uint32_t *__restrict__ counters, int rev, uint32_t block_len) {
+                    uint32_t *__restrict__ counters, uint32_t small_cap, int rev, uint32_t block_len) {
     __shared__ Anchor a[FINALIZE_CAP];
     __shared__ Anchor b[FINALIZE_CAP];
     __shared__ uint32_t kept, kept2;
     const uint32_t n = counters[0]; // CTR_ANCHORS
-    if (n > FINALIZE_CAP || n > anchor_cap) {
+    if (n > small_cap || n > anchor_cap) {
         if (threadIdx.x == 0) counters[6] = 0xFFFFFFFFu;
         return;
     }
@@ -271,6 +271,59 @@ k_finalize_small_rm(const Anchor *__restrict__ anchors, uint32_t anchor_cap, sa_
         out[i] = s;
     }
     if (threadIdx.x == 0) counters[6] = k;
+}
+
+} // namespace sa
+
+
+// ---------------------------------------------------------------------------------------------
+// Device-wide path (more than FINALIZE_CAP anchors): stable LSD radix passes (cub::DeviceRadixSort)
+// over the composite key of each order, 64 bits per pass, least significant word first, carrying a
+// permutation.  Every order above is a lexicographic order of 32-bit fields (descending fields are
+// stored inverted), so three 64-bit words hold it:
+//   ORD_DIAG      hspComp       [tag, diagonal] [ref_start, len]      [~score]
+//   ORD_LASTZ     hspCompLastz  [tag, query]    [ref_start, len]      [~score]
+//   ORD_RM_FIRST  :819          [tag, query]    [~len, ref_start]     [~score]
+//   ORD_RM_DIAG   :825          [tag, diagonal] [ref_start, query]    [~score, ~len]
+//   ORD_RM_FINAL  :833          [tag, query]    [~score, ~ref_start]  [~len]
+namespace sa {
+
+enum { ORD_DIAG = 0, ORD_LASTZ = 1, ORD_RM_FIRST = 2, ORD_RM_DIAG = 3, ORD_RM_FINAL = 4 };
+
+__device__ __forceinline__ unsigned long long anchor_key_word(const Anchor &a, int order, int word) {
+    const uint32_t diag = a.ref_start - a.query_start;
+    const uint32_t nscore = ~((uint32_t)a.score ^ 0x80000000u); // descending signed score as ascending unsigned
+    uint32_t hi = 0, lo = 0;
+    if (word == 0) { hi = a.tag; lo = (order == ORD_DIAG || order == ORD_RM_DIAG) ? diag : a.query_start; }
+    else if (word == 1) {
+        if (order == ORD_DIAG || order == ORD_LASTZ) { hi = a.ref_start; lo = a.len; }
+        else if (order == ORD_RM_FIRST) { hi = ~a.len; lo = a.ref_start; }
+        else if (order == ORD_RM_DIAG) { hi = a.ref_start; lo = a.query_start; }
+        else { hi = nscore; lo = ~a.ref_start; }
+    } else {
+        if (order == ORD_RM_DIAG) { hi = nscore; lo = ~a.len; }
+        else if (order == ORD_RM_FINAL) { hi = ~a.len; lo = 0; }
+        else { hi = nscore; lo = 0; }
+    }
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// keys of one pass for the anchors in their current permutation (perm == nullptr: identity, and writes it)
+__global__ void __launch_bounds__(256)
+k_anchor_keys(const Anchor *__restrict__ a, const uint32_t *__restrict__ perm_in, uint32_t n, int order, int word,
+              unsigned long long *__restrict__ keys, uint32_t *__restrict__ perm_out) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t src = perm_in ? perm_in[i] : i;
+        keys[i] = anchor_key_word(a[src], order, word);
+        if (!perm_in) perm_out[i] = i;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_anchor_gather(const Anchor *__restrict__ a, const uint32_t *__restrict__ perm, uint32_t n, Anchor *__restrict__ out) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[perm[i]];
 }
 
 } // namespace sa

@@ -21,7 +21,6 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -156,6 +155,7 @@ struct Global {
     int extend_grid = 0;
     int wide_grid = 0;         // k_extend_wide (warp per hit), SEGALIGN_B200_WIDE=0 sends all survivors to k_extend_hits
     bool use_wide = true;
+    uint32_t finalize_cap = FINALIZE_CAP; // anchors one block sorts in shared memory; more take the device-wide radix path (SEGALIGN_B200_FINALIZE_CAP lowers it: tests)
     uint32_t merge_min = 65536; // calls with more filter survivors than this take the merge pass (SEGALIGN_B200_MERGE_MIN, 0 = never)
     bool use_compact = true;   // SEGALIGN_B200_COMPACT_SEEDS=0: always copy seed vectors as they are
     uint32_t ref_len = 0;
@@ -381,22 +381,24 @@ struct PhaseTimer {
     }
 };
 
-template <typename Comp>
-int sort_anchors_by(Workspace *w, Anchor *keys, uint32_t n, Comp comp) {
+// Device-wide sort of n anchors under one of the orders of kernels_sort.cuh: three stable 64-bit radix passes
+// (least significant key word first) over a permutation, then one gather.  in -> out (distinct buffers).
+int radix_sort_anchors(Workspace *w, const Anchor *in, Anchor *out, uint32_t n, int order) {
+    cudaStream_t st = w->stream;
+    if (n == 0) return SA_OK;
+    TRY(ensure(w->d_mkeys, w->mkeys_cap, 2 * (size_t)n, "sort_keys"));
+    TRY(ensure(w->d_midx, w->midx_cap, 2 * (size_t)n, "sort_index"));
+    cub::DoubleBuffer<unsigned long long> dk(w->d_mkeys, w->d_mkeys + n);
+    cub::DoubleBuffer<uint32_t> dv(w->d_midx, w->d_midx + n);
     size_t bytes = 0;
-    CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, comp, w->stream), SA_ERR_KERNEL);
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, bytes, dk, dv, (int)n, 0, 64, st), SA_ERR_KERNEL);
     TRY(ensure(w->d_temp, w->temp_cap, bytes, "sort_temp"));
-    CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, comp, w->stream), SA_ERR_KERNEL);
-    return SA_OK;
-}
-
-int sort_anchors(Workspace *w, Anchor *keys, uint32_t n, bool lastz) {
-    size_t bytes = 0;
-    if (lastz) CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, CompLastz(), w->stream), SA_ERR_KERNEL);
-    else CU(cub::DeviceMergeSort::SortKeys(nullptr, bytes, keys, (int64_t)n, CompDiag(), w->stream), SA_ERR_KERNEL);
-    TRY(ensure(w->d_temp, w->temp_cap, bytes, "sort_temp"));
-    if (lastz) CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, CompLastz(), w->stream), SA_ERR_KERNEL);
-    else CU(cub::DeviceMergeSort::SortKeys(w->d_temp, bytes, keys, (int64_t)n, CompDiag(), w->stream), SA_ERR_KERNEL);
+    for (int word = 2; word >= 0; word--) {
+        k_anchor_keys<<<grid_for(n, 256), 256, 0, st>>>(in, word == 2 ? nullptr : dv.Current(), n, order, word, dk.Current(), dv.Current());
+        CU(cub::DeviceRadixSort::SortPairs(w->d_temp, bytes, dk, dv, (int)n, 0, 64, st), SA_ERR_KERNEL);
+    }
+    k_anchor_gather<<<grid_for(n, 256), 256, 0, st>>>(in, dv.Current(), n, out);
+    CU(cudaGetLastError(), SA_ERR_KERNEL);
     return SA_OK;
 }
 
@@ -608,8 +610,8 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
         pt.mark(PH_EXTEND);
         // 5. diagonal sort, dedupe, final order (seed_filter.cu:776-782): one block when the anchors
         //    fit; the counters, the plan and the first FINALIZE_CAP records come back together
-        if (in.rm) k_finalize_small_rm<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters, rev, g.ref.len);
-        else k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters);
+        if (in.rm) k_finalize_small_rm<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters, G.finalize_cap, rev, g.ref.len);
+        else k_finalize_small<<<1, FINALIZE_THREADS, 0, st>>>(w->d_anchors_a, anchor_cap, w->d_out, w->d_counters, G.finalize_cap);
         pt.mark(PH_SORT);
         launches += 2;
         CU(cudaMemcpyAsync(w->h_small, w->d_counters, CTR_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
@@ -676,34 +678,34 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
                 return SA_OK;
             };
             if (rev) k_rm_to_forward<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, g.ref.len);
-            TRY(sort_anchors_by(w, w->d_anchors_a, n_pre, CompRmFirst()));
             TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
+            TRY(radix_sort_anchors(w, w->d_anchors_a, w->d_anchors_b, n_pre, ORD_RM_FIRST));
             CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
-            k_dedupe_exact<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + CTR_DEDUPE);
+            k_dedupe_exact<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_b, n_pre, w->d_anchors_a, w->d_counters + CTR_DEDUPE);
             uint32_t n1 = 0;
             TRY(count_of(n1));
-            TRY(sort_anchors_by(w, w->d_anchors_b, n1, CompRmDiag()));
+            TRY(radix_sort_anchors(w, w->d_anchors_a, w->d_anchors_b, n1, ORD_RM_DIAG));
             CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
             k_dedupe<<<grid_for(n1, 256), 256, 0, st>>>(w->d_anchors_b, n1, w->d_anchors_a, w->d_counters + CTR_DEDUPE);
             TRY(count_of(n_final));
-            TRY(sort_anchors_by(w, w->d_anchors_a, n_final, CompRmFinal()));
+            TRY(radix_sort_anchors(w, w->d_anchors_a, w->d_anchors_b, n_final, ORD_RM_FINAL));
             TRY(ensure(w->d_out, w->out_cap, n_final, "hsp_out"));
-            k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_a, n_final, w->d_out);
-            launches += 14;
+            k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_b, n_final, w->d_out);
+            launches += 3 * 32 + 5;
             pt.mark(PH_SORT);
         } else {
-            // many distinct anchors (repeat families, forced small iterations): device-wide sorts
-            TRY(sort_anchors(w, w->d_anchors_a, n_pre, false));
+            // many distinct anchors (repeat families, forced small iterations): device-wide radix sorts
             TRY(ensure(w->d_anchors_b, w->anchors_b_cap, n_pre, "hsp_unique"));
+            TRY(radix_sort_anchors(w, w->d_anchors_a, w->d_anchors_b, n_pre, ORD_DIAG));
             CU(cudaMemsetAsync(w->d_counters + CTR_DEDUPE, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
-            k_dedupe<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_a, n_pre, w->d_anchors_b, w->d_counters + CTR_DEDUPE);
+            k_dedupe<<<grid_for(n_pre, 256), 256, 0, st>>>(w->d_anchors_b, n_pre, w->d_anchors_a, w->d_counters + CTR_DEDUPE);
             CU(cudaMemcpyAsync(w->h_small, w->d_counters + CTR_DEDUPE, sizeof(uint32_t), cudaMemcpyDeviceToHost, st), SA_ERR_MEMCPY);
             CU(cudaStreamSynchronize(st), SA_ERR_KERNEL);
             n_final = w->h_small[0];
-            TRY(sort_anchors(w, w->d_anchors_b, n_final, true));
+            TRY(radix_sort_anchors(w, w->d_anchors_a, w->d_anchors_b, n_final, ORD_LASTZ));
             TRY(ensure(w->d_out, w->out_cap, n_final, "hsp_out"));
             k_strip_tags<<<grid_for(n_final, 256), 256, 0, st>>>(w->d_anchors_b, n_final, w->d_out);
-            launches += 8;
+            launches += 2 * 32 + 4;
             pt.mark(PH_SORT);
         }
     }
@@ -886,6 +888,7 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         G.wide_grid = 4 * std::max(1, sms);   // four-warp blocks, one warp per hit
         if (const char *e = getenv("SEGALIGN_B200_WIDE_CTAS")) if (atoi(e) > 0) G.wide_grid = atoi(e) * std::max(1, sms);
         { const char *e = getenv("SEGALIGN_B200_WIDE"); G.use_wide = !(e && atoi(e) == 0); }
+        { const char *e = getenv("SEGALIGN_B200_FINALIZE_CAP"); G.finalize_cap = e ? std::min<uint32_t>((uint32_t)FINALIZE_CAP, (uint32_t)strtoul(e, nullptr, 10)) : (uint32_t)FINALIZE_CAP; }
         { const char *e = getenv("SEGALIGN_B200_MERGE_MIN"); G.merge_min = e ? (uint32_t)strtoul(e, nullptr, 10) : 65536u; }
         { const char *e = getenv("SEGALIGN_B200_COMPACT_SEEDS"); G.use_compact = !(e && atoi(e) == 0); }
         // blocks uploaded before the matrix was known carry records built for another terminator set

@@ -374,3 +374,14 @@ def test_merge_pass_collapses_a_self_alignment(backend, monkeypatch):
     assert st["merge_calls"] >= 1
     # ~30 k main-diagonal survivors on the plus strand collapse to a handful of representatives
     assert st["merge_dropped"] > 0.9 * (query.size - span)
+
+
+@pytest.mark.parametrize("case", H.CASES, ids=lambda c: c.name)
+def test_device_wide_radix_sort_path_matches_reference_golden(backend, case, monkeypatch):
+    """SEGALIGN_B200_FINALIZE_CAP=8: calls with more than 8 anchors skip the one-block bitonic finalisation
+    and take the device-wide path -- stable 64-bit radix passes over the composite keys of
+    src/seed_filter.cu:54-108, predecessor dedupe, radix passes for the final order."""
+    monkeypatch.setenv("SEGALIGN_B200_FINALIZE_CAP", "8")
+    want, _ = H.golden_as_calls(case)
+    got = H.run_backend(backend, case, device_seeding=True)
+    H.assert_calls_equal(got, want, "device-wide radix sort path vs reference golden")

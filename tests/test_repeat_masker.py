@@ -89,10 +89,12 @@ def test_rm_backend_matches_reference_golden(backend, case, prop, device_seeding
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,prop", H.RM_CASES, ids=RM_IDS)
 @pytest.mark.parametrize("knob", ["SEGALIGN_B200_FUSED=0", "SEGALIGN_B200_FILTER=0", "SEGALIGN_B200_FILTER_KERNEL=2",
-                                  "SEGALIGN_B200_MERGE_MIN=8", "SEGALIGN_B200_MERGE_MIN=0", "SEGALIGN_B200_DEDUP=0"])
+                                  "SEGALIGN_B200_MERGE_MIN=8", "SEGALIGN_B200_MERGE_MIN=0", "SEGALIGN_B200_DEDUP=0",
+                                  "SEGALIGN_B200_FINALIZE_CAP=8"])
 def test_rm_backend_code_paths_match_reference_golden(backend, case, prop, knob, monkeypatch):
     """General (materialised hit list) path, exact stage alone, tile-walk-only filter, merge pass forced
-    / disabled, no duplicate table: all must give the reference's bytes."""
+    / disabled, no duplicate table, device-wide radix sorts instead of the one-block finalisation: all must
+    give the reference's bytes."""
     k, v = knob.split("=")
     monkeypatch.setenv(k, v)
     want, _ = H.load_rm_golden(case)
