@@ -165,7 +165,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     const uint64_t *rp2_m4 = P.rp2 - 4; // 16-byte aligned start of the plane's front padding (REC_FRONT = 4 words)
     static_assert(REC_FRONT == 4, "the window fetch below starts at word (w + 1) & ~1 of the padded plane");
 #if SA_SCR_L2_HINTS
-    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    const uint64_t pol_stream = l2_policy_evict_first();
 #endif
 
     const uint32_t n_var = SRC == SRC_RANGE ? H.per : 1u;       // bucket sets per group (device seeding: 1 + transition variants)
@@ -210,11 +210,11 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             if (hs < n && (rc < 3u || (w1 & 1u))) {
                 const uint64_t *src = rp2_m4 + ((w1 & ~1u) + 2u * rc);
                 uint4 *dst = stage + hs * SCR_STAGE_STRIDE + (rc ^ ((hs >> 1) & 3u));
-#if SA_SCR_L2_HINTS
-                cp_async16_hint(dst, src, pol_keep);
-#else
+                // no L2 policy operand here: with `.L2::cache_hint` ptxas 12.9 emits, for the three copies whose
+                // shared address is the first one's plus an immediate, an LDGSTS form that reads an unset uniform
+                // register pair as descriptor (cuobjdump: `[R41+UR0+0x200], desc[UR1]`) -- the launch dies with
+                // "illegal instruction".  The hint bought nothing measurable.
                 cp_async16(dst, src);
-#endif
             }
         }
     };

@@ -67,3 +67,18 @@ def test_product_never_imports_oracle():
             text = p.read_text()
             for pat in (r'#\s*include\s*[<"][^>"]*oracle', r"^\s*(from|import)\s+oracle\b", r"libsa_oracle", r"dlopen"):
                 assert not re.search(pat, text, flags=re.M), (p, pat)
+
+
+def test_sass_has_no_misencoded_async_copies(built):
+    """ptxas 12.9 mis-encodes `cp.async ... L2::cache_hint` copies whose shared address is a previous copy's
+    plus an immediate: the LDGSTS then names an unset, odd uniform register as its descriptor
+    (`[R41+UR0+0x200], desc[UR1]`) and the launch dies with "illegal instruction" (seen on a B200, round 2).
+    Every 64-bit descriptor operand in the library's SASS must be an even uniform register."""
+    import re
+    import subprocess
+    from segalign_b200.backend import LIB_PATH
+    sass = subprocess.run(["cuobjdump", "-sass", str(LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    ops = [l for l in sass.splitlines() if re.search(r"\b(LDGSTS|LDG|STG|ATOMG|REDG)\b", l) and "desc[" in l]
+    assert len(ops) > 100
+    bad = [l.strip() for l in ops if int(re.search(r"desc\[UR(\d+)\]", l).group(1)) % 2]
+    assert not bad, bad[:5]
