@@ -137,6 +137,17 @@ def gen_repeats(rng, n=200_000, d=0.3, copies=150, elem=300, elem_div=0.1, low_c
     return ref, q
 
 
+def gen_inverted_repeats(rng, n=30_000, copies=30, elem=300, elem_div=0.08):
+    """One sequence with a repeat family whose copies sit on BOTH strands (every other copy is
+    reverse-complemented): a self-alignment then has minus-strand HSPs (repeat-masker variant)."""
+    seq = genome.random_genome(n, rng)
+    element = genome.random_genome(elem, rng)
+    for k, s in enumerate(rng.integers(0, n - elem, size=copies)):
+        copy = genome.mutate(element, elem_div, rng)
+        seq[s:s + elem] = genome.revcomp_ascii(copy) if k & 1 else copy
+    return seq, seq.copy()
+
+
 def gen_random_pair(rng, n_ref=400_000, n_query=100_000):
     """Unrelated sequences: only random hits, nothing passes (zero-anchor iterations)."""
     return genome.random_genome(n_ref, rng), genome.random_genome(n_query, rng)
@@ -149,6 +160,7 @@ GENERATORS = {
     "shared_ambiguous": gen_shared_ambiguous,
     "repeats": gen_repeats,
     "random_pair": gen_random_pair,
+    "inverted_repeats": gen_inverted_repeats,
 }
 
 # Small cases: the CPU oracle finishes each in seconds.  Golden dumps of the UNMODIFIED
@@ -428,6 +440,9 @@ RM_CASES = [
           wga_chunk=6_000, max_hits_override=900), 0.6),
     (Case("rm_plus_only_noentropy", "repeats", dict(n=26_000, copies=24, low_complexity=12), rng_seed=34, strand="plus",
           noentropy=True, lastz_interval=8_000), 0.3),
+    (Case("rm_inverted_repeats", "inverted_repeats", rng_seed=36, lastz_interval=11_000, wga_chunk=4_000), 0.6),
+    (Case("rm_inverted_multi_iter", "inverted_repeats", dict(n=24_000, copies=24), rng_seed=37, lastz_interval=13_000,
+          wga_chunk=6_500, max_hits_override=700), 1.0),
     (Case("rm_iupac_notransition", "shared_ambiguous", dict(n=30_000, runs=20), rng_seed=35, transition=False, strand="plus",
           ambiguous="iupac", hspthresh=2200, lastz_interval=10_000, wga_chunk=4_000), 0.7),
 ]
@@ -543,12 +558,17 @@ def run_rm_cpu_oracle(case: Case, neigh_prop: float, seq=None, max_hits_device: 
     table = sao.Table(shape, seq, seq.size, case.step)
     enc = sao.encode(seq)
     enc_rc = sao.rm_revcomp_codes(enc)
-    rc_ascii = sao.revcomp_ascii(seq)     # host RevComp: what the seeder reads minus-strand seeds from
+    # host RevComp: what the seeder reads minus-strand seeds from.  The last minus-strand chunk runs up to
+    # position len-1 (seeder.cpp:110-111), i.e. its seed spans reach past the sequence into the zero-filled
+    # DRAM arena: both host buffers get that zero tail here
+    tail = np.zeros(64, dtype=np.uint8)
+    rc_ascii = np.concatenate([sao.revcomp_ascii(seq), tail])
+    seq_padded = np.concatenate([seq, tail])
     mh = case.max_hits_override if case.max_hits_override > 0 else max_hits_device
     params = sao.make_params(matrix_for(case), case.xdrop, case.hspthresh, case.noentropy, shape.span, mh)
     out = []
     for rev, j0, j1, rs, re_ in rm_calls(case, seq.size, shape.span, neigh_prop):
-        seeds = shape.chunk_seeds(rc_ascii if rev else seq, j0, j1, case.transition)
+        seeds = shape.chunk_seeds(rc_ascii if rev else seq_padded, j0, j1, case.transition)
         if seeds.size == 0:
             continue
         res = sao.rm_seed_and_filter(params, table, enc, enc_rc, seeds, bool(rev), rs, re_)
