@@ -621,6 +621,11 @@ def reference_gpu_leg(be, wl, span, args):
             "gbp_per_s": round(qn / ref_s / 1e9, 6) if ref_s > 0 else None,
             "reference_table_build_s": round(float(dump.times[1]), 3),
             "reference_host_seedgen_s": round(float(dump.times[3]), 3),
+            "reference_seeder_positions_per_s_per_thread": round(2.0 * qn / max(1e-9, float(dump.times[3])), 1),
+            "reference_seeder_bound_gbp_per_s": round(host_threads(args, 1) * qn / max(1e-9, float(dump.times[3])) / 1e9, 4),
+            "reference_seeder_note": "src/seeder.cpp:57-74 (GetKmerIndexAtPos + push_back per seed word) as the runner executes "
+                                     "it, one thread; x %d threads = the most query the UNMODIFIED host loop can hand to any "
+                                     "backend through g_SeedAndFilter on this box (compare e2e.vector_abi)" % host_threads(args, 1),
             "runner_wall_s": round(t_total, 1),
             "what": "oracle/_ref/oracle_runner = the reference's unmodified seed_filter.cu / seed_pos_table.cu / "
                     "seed_filter_interface.cu (sm_100a build) on the same GPU, one call at a time through g_SeedAndFilter; "

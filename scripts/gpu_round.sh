@@ -43,6 +43,21 @@ d=json.load(open("$OUT/${TAG}_bench_ce11.json")); r=d["roofline"]
 print("CE11 value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "vec", d["e2e"]["vector_abi"]["value"],
       "frac", r["frac"], "launch_ms", r["avg_launch_ms"], "whole", r["whole_step"]["frac"], "hits/s", d["rates"]["hits_per_s"])
 PY
+if [ -n "$VARIANTS" ]; then   # "name:nvcc flags;name:flags": rebuild on the box and bench each variant (lean), then restore
+  IFS=';' read -ra VARS <<< "$VARIANTS"
+  for V in "${VARS[@]}"; do
+    NAME=${V%%:*}; FLAGS=${V#*:}
+    SEGALIGN_B200_NVCC_EXTRA="$FLAGS" python -c "from segalign_b200.build import build_backend; build_backend(force=True)" || exit 1
+    for W in syn500 ce11; do
+      timeout 400 python bench.py --workload $W --steps $STEPS --warmup 3 $LEAN > $OUT/${TAG}_bench_${W}_$NAME.json 2> $OUT/${TAG}_bench_${W}_$NAME.err || { echo "variant $NAME $W failed"; tail -3 $OUT/${TAG}_bench_${W}_$NAME.err; continue; }
+      python -c "
+import json
+d=json.load(open('$OUT/${TAG}_bench_${W}_$NAME.json')); r=d['roofline']
+print('VARIANT $NAME $W value', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', r['frac'], 'launch_ms', r['avg_launch_ms'], 'whole', r['whole_step']['frac'])"
+    done
+  done
+  python -c "from segalign_b200.build import build_backend; build_backend(force=True)"
+fi
 if [ -z "$SKIP_NCU" ]; then
   for W in ${NCU_WORKLOADS:-syn500}; do
     QMB=8; [ "$W" = "syn500" ] && QMB=4

@@ -47,7 +47,10 @@ constexpr int SCR_THREADS = SA_SCR_THREADS;
 constexpr int SCR_STAGE_STRIDE = SA_SCR_STAGE_STRIDE; // uint4 slots per hit in the staging buffer: four 16-byte chunks, XOR-swizzled
 static_assert(SCR_STAGE_STRIDE == 4, "the swizzle below assumes 64-byte staging rows");
 constexpr int SCR_ROW_STRIDE = SCREEN_ROW_WORDS; // 48 bytes: conflict-free for 16-byte reads
-constexpr int SCR_RING = 256;        // staged hits per warp (ring, power of two)
+#ifndef SA_SCR_RING
+#define SA_SCR_RING 256
+#endif
+constexpr int SCR_RING = SA_SCR_RING; // staged hits per warp (ring, power of two)
 constexpr int SCR_ROWS = 64;         // aligned query rows per warp (ring, power of two)
 constexpr int SCR_REFILL = 96;       // refill the ring when fewer hits than this are staged (three rounds:
                                      // the positions of round n+1 were copied in before the refill of round n)
@@ -111,6 +114,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ uint4 lds_v4(const uint4 *p) {
+    uint4 v;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
     ScreenRec r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
     return r;
@@ -405,7 +414,10 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             {
                 const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
                 const uint32_t sw = (lane >> 1) & 3u;
-                const uint4 m0 = mine[0u ^ sw], m1 = mine[1u ^ sw], m2 = mine[2u ^ sw], m3 = mine[3u ^ sw];
+                // explicit 128-bit loads: left to itself the compiler reads the seven 64-bit words it needs with
+                // LDS.64, and lanes L and L+8 then meet in one bank pair (the swizzle is per 16-byte chunk)
+                const uint4 m0 = lds_v4(mine + (0u ^ sw)), m1 = lds_v4(mine + (1u ^ sw)), m2 = lds_v4(mine + (2u ^ sw)),
+                            m3 = lds_v4(mine + (3u ^ sw));
                 const uint64_t c[8] = {(uint64_t)m0.x | ((uint64_t)m0.y << 32), (uint64_t)m0.z | ((uint64_t)m0.w << 32),
                                        (uint64_t)m1.x | ((uint64_t)m1.y << 32), (uint64_t)m1.z | ((uint64_t)m1.w << 32),
                                        (uint64_t)m2.x | ((uint64_t)m2.y << 32), (uint64_t)m2.z | ((uint64_t)m2.w << 32),

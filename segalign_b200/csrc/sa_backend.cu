@@ -874,11 +874,11 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         CU(cudaFuncSetAttribute(k_filter_hits3<SRC_SEEDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCR_SMEM_BYTES), SA_ERR_KERNEL);
         int per_sm3 = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, k_filter_hits3<SRC_RANGE>, SCR_THREADS, SCR_SMEM_BYTES), SA_ERR_KERNEL);
-        // Two of the three block slots per SM by default: the third is left to the next call's kernel
+        // All but one of the block slots per SM by default (2 of 3): the last is left to the next call's kernel
         // (another stream), whose head overlaps this one's tail -- 8 % more calls per second with 16
         // callers than three blocks per SM, at 6 % more time for a launch that runs alone.
         G.filter3_grid_alone = std::max(1, per_sm3) * std::max(1, sms);
-        per_sm3 = std::min(per_sm3, 2);
+        per_sm3 = std::max(1, per_sm3 - 1);
         if (const char *e = getenv("SEGALIGN_B200_FILTER_CTAS")) if (atoi(e) > 0) { per_sm3 = atoi(e); G.filter3_grid_alone = per_sm3 * std::max(1, sms); }
         G.filter3_grid = std::max(1, per_sm3) * std::max(1, sms);
         G.filter_kernel = 3;
