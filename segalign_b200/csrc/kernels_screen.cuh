@@ -114,11 +114,43 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ uint4 lds_v4(const uint4 *p) {
+// Shared-memory accesses of the hot loop by 32-bit shared-space address (computed once per warp): through
+// generic pointers ptxas re-derives the shared window base (S2R SR_CgaCtaId + LEA ...) at every access site,
+// ~20 instructions per round.
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
+}
+__device__ __forceinline__ uint32_t lds_b32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_b16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_b8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_b16(uint32_t a, uint32_t x) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)x) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_hint_s(uint32_t smem_dst, const void *gmem_src, uint64_t policy) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gmem_src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ ScreenRec as_rec(const uint4 v) {
     ScreenRec r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
@@ -171,6 +203,9 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     // prefix, and (device seeding) the row id of its query position
     uint32_t *ownerdelta = reinterpret_cast<uint32_t *>(smem + SCR_OFF_DELTA) + warp * SCR_ROWS;
     uint8_t *ownerrow = reinterpret_cast<uint8_t *>(ownerdelta + 32);
+    const uint32_t sa_stage = (uint32_t)__cvta_generic_to_shared(stage), sa_rows = (uint32_t)__cvta_generic_to_shared(rows),
+                   sa_ring = (uint32_t)__cvta_generic_to_shared(ring_r), sa_meta = (uint32_t)__cvta_generic_to_shared(ring_meta),
+                   sa_q = (uint32_t)__cvta_generic_to_shared(myq), sa_delta = (uint32_t)__cvta_generic_to_shared(ownerdelta);
     const uint64_t *rp2_m4 = P.rp2 - 4; // 16-byte aligned start of the plane's front padding (REC_FRONT = 4 words)
     static_assert(REC_FRONT == 4, "the window fetch below starts at word (w + 1) & ~1 of the padded plane");
 #if SA_SCR_L2_HINTS
@@ -218,12 +253,12 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             const uint32_t w1 = (r >> 5) + 1u; // = (w - 3) + REC_FRONT
             if (hs < n && (rc < 3u || (w1 & 1u))) {
                 const uint64_t *src = rp2_m4 + ((w1 & ~1u) + 2u * rc);
-                uint4 *dst = stage + hs * SCR_STAGE_STRIDE + (rc ^ ((hs >> 1) & 3u));
+                const uint32_t dst = sa_stage + (hs * SCR_STAGE_STRIDE + (rc ^ ((hs >> 1) & 3u))) * 16u;
                 // no L2 policy operand here: with `.L2::cache_hint` ptxas 12.9 emits, for the three copies whose
                 // shared address is the first one's plus an immediate, an LDGSTS form that reads an unset uniform
                 // register pair as descriptor (cuobjdump: `[R41+UR0+0x200], desc[UR1]`) -- the launch dies with
                 // "illegal instruction".  The hint bought nothing measurable.
-                cp_async16(dst, src);
+                cp_async16_s(dst, src);
             }
         }
     };
@@ -364,12 +399,13 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 const uint32_t j = j0 + __popc(bounds & lt_mask);
                 if (kk * 32u + lane < cnt) {
                     const uint32_t slot = (tail + kk * 32u + lane) & (uint32_t)(SCR_RING - 1);
+                    const uint32_t od = lds_b32(sa_delta + j * 4u), orow = lds_b8(sa_delta + 128u + j);
 #if SA_SCR_L2_HINTS
-                    cp_async4_hint(ring_r + slot, H.pos_table + (ownerdelta[j] + f0 + lane), pol_stream);
+                    cp_async4_hint_s(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane), pol_stream);
 #else
-                    cp_async4(ring_r + slot, H.pos_table + (ownerdelta[j] + f0 + lane));
+                    cp_async4_s(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane));
 #endif
-                    ring_meta[slot] = (uint16_t)(ownerrow[j] | vtag);
+                    sts_b16(sa_meta + slot * 2u, orow | vtag);
                 }
             }
             __syncwarp();
@@ -388,7 +424,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 __syncwarp();
                 n1 = min(tail - head, 32u);
                 safe_tail = tail;
-                r_next = lane < n1 ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
+                r_next = lane < n1 ? lds_b32(sa_ring + ((head + lane) & (uint32_t)(SCR_RING - 1)) * 4u) + H.seed_size : 0u;
                 if (P.ref_has_soft) soft_next = lane < n1 && soft_window(P.rsoft, r_next);
                 request_records(r_next, n1);
                 cp_async_commit();
@@ -396,28 +432,44 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             } else {
                 cp_async_wait_group<1>(); // everything but this refill's positions has landed
             }
+            __syncwarp(); // ... for every lane: a window is written by four other lanes' copies
+            // Order of the round: the shared-memory loads whose results are needed first are issued first and
+            // the NEXT round's gathers leave as soon as this round's staged windows sit in registers -- before the
+            // ~45 instructions of window alignment, not after them (ncu at a 500 Mb block: 13 % of the round's
+            // stall samples sat on the wait above, the gathers of a round being only ~250 instructions ahead).
+            const uint32_t r0 = r_next;      // this lane's anchor: read when its window was requested
+            const bool soft0 = soft_next;
             // (a hit outside the caller's reference window -- repeat-masker variant -- is counted, not screened)
-            const bool have = lane < n1 && r_next - H.win_lo <= H.win_hi - H.win_lo;
-            uint32_t r0 = 0, rowid = 0, vkey = 0;
+            const bool have = lane < n1 && r0 - H.win_lo <= H.win_hi - H.win_lo;
+            const uint32_t head_next = head + n1;
+            const uint32_t pre_next = min(safe_tail - head_next, 32u); // only positions that are known to have landed
+            uint32_t r_nn = 0;
+            if (lane < pre_next) r_nn = lds_b32(sa_ring + ((head_next + lane) & (uint32_t)(SCR_RING - 1)) * 4u);
+            uint32_t rowid = 0, vkey = 0;
             if (have) {
-                const uint32_t meta = ring_meta[(head + lane) & (uint32_t)(SCR_RING - 1)];
+                const uint32_t meta = lds_b16(sa_meta + ((head + lane) & (uint32_t)(SCR_RING - 1)) * 2u);
                 rowid = meta & 0xFFu;
                 vkey = meta >> 8;
             }
-            const uint4 *qrow = reinterpret_cast<const uint4 *>(rows + (rowid & (uint32_t)(SCR_ROWS - 1)) * SCR_ROW_STRIDE);
-            const uint4 q_a = qrow[0], q_b = qrow[1], q_c = qrow[2];
+            const uint32_t mine = sa_stage + lane * (SCR_STAGE_STRIDE * 16u);
+            const uint32_t sw = (lane >> 1) & 3u;
+            // explicit 128-bit loads: left to itself the compiler reads the seven 64-bit words it needs with
+            // LDS.64, and lanes L and L+8 then meet in one bank pair (the swizzle is per 16-byte chunk)
+            const uint4 m0 = lds_v4(mine + (0u ^ sw) * 16u), m1 = lds_v4(mine + (1u ^ sw) * 16u), m2 = lds_v4(mine + (2u ^ sw) * 16u),
+                        m3 = lds_v4(mine + (3u ^ sw) * 16u);
+            __syncwarp(); // every lane holds its window: the staging buffer is free again
+            head = head_next;
+            pre_n = pre_next;
+            r_next = lane < pre_n ? r_nn + H.seed_size : 0u;
+            if (P.ref_has_soft) soft_next = lane < pre_n && soft_window(P.rsoft, r_next);
+            if (pre_n) request_records(r_next, pre_n);
+            cp_async_commit(); // group "R": the records of the next round
+            const uint32_t qrow = sa_rows + (rowid & (uint32_t)(SCR_ROWS - 1)) * (SCR_ROW_STRIDE * 4u);
+            const uint4 q_a = lds_v4(qrow), q_b = lds_v4(qrow + 16u), q_c = lds_v4(qrow + 32u);
             const uint32_t qr[SCREEN_ROW_WORDS] = {q_a.x, q_a.y, q_a.z, q_a.w, q_b.x, q_b.y, q_b.z, q_b.w, q_c.x, q_c.y, q_c.z, 0u};
             const uint32_t key = q_c.w + vkey; // seed order index of the hit's seed word
-            __syncwarp();
-            r0 = r_next; // this lane's anchor: read when the records were requested
             uint32_t rr[SCREEN_ROW_WORDS];
             {
-                const uint4 *mine = stage + lane * SCR_STAGE_STRIDE;
-                const uint32_t sw = (lane >> 1) & 3u;
-                // explicit 128-bit loads: left to itself the compiler reads the seven 64-bit words it needs with
-                // LDS.64, and lanes L and L+8 then meet in one bank pair (the swizzle is per 16-byte chunk)
-                const uint4 m0 = lds_v4(mine + (0u ^ sw)), m1 = lds_v4(mine + (1u ^ sw)), m2 = lds_v4(mine + (2u ^ sw)),
-                            m3 = lds_v4(mine + (3u ^ sw));
                 const uint64_t c[8] = {(uint64_t)m0.x | ((uint64_t)m0.y << 32), (uint64_t)m0.z | ((uint64_t)m0.w << 32),
                                        (uint64_t)m1.x | ((uint64_t)m1.y << 32), (uint64_t)m1.z | ((uint64_t)m1.w << 32),
                                        (uint64_t)m2.x | ((uint64_t)m2.y << 32), (uint64_t)m2.z | ((uint64_t)m2.w << 32),
@@ -426,22 +478,12 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 uint64_t a[SCREEN_RECS];
 #pragma unroll
                 for (int j = 0; j < SCREEN_RECS; j++) a[j] = par ? c[j + 1] : c[j];
-                screen_align_p2(a, r0 & 31u, soft_next, rr);
+                screen_align_p2(a, r0 & 31u, soft0, rr);
             }
-            __syncwarp(); // every lane holds its window: the staging buffer is free again
-            head += n1;
-            pre_n = min(safe_tail - head, 32u); // only positions that are known to have landed
-            r_next = lane < pre_n ? ring_r[(head + lane) & (uint32_t)(SCR_RING - 1)] + H.seed_size : 0u;
-            if (P.ref_has_soft) soft_next = lane < pre_n && soft_window(P.rsoft, r_next);
-            if (pre_n) request_records(r_next, pre_n);
-            cp_async_commit(); // group "R": the records of the next round
             int bound; bool decided;
             const bool push = have && !screen_reject(rr, qr, C, bound, decided);
             const unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
-            if (push) {
-                const uint32_t idx = qcount + __popc(pm & lt_mask);
-                myq[idx * 2 + 0] = r0; myq[idx * 2 + 1] = key;
-            }
+            if (push) sts_v2(sa_q + (qcount + __popc(pm & lt_mask)) * 8u, r0, key);
             qcount += __popc(pm);
             acc_walked += __popc(pm);
             __syncwarp();

@@ -528,10 +528,6 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             CU(cudaMemsetAsync(w->d_counters + CTR_OUT, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
             CU(cudaMemsetAsync(w->d_counters + CTR_SURV2, 0, sizeof(uint32_t), st), SA_ERR_MEMCPY);
         }
-        if (D.mask) {
-            CU(cudaMemsetAsync(w->d_dedup, 0xFF, (size_t)kDedupSlots * 16, st), SA_ERR_MEMCPY);
-            CU(cudaMemsetAsync(D.tagbits, 0, (size_t)kDedupSlots * 4, st), SA_ERR_MEMCPY);
-        }
         if (merged) {
             // stage A already ran: its survivors were reduced to one representative per all-match chain
         } else if (fused) {
@@ -588,6 +584,10 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
             }
         }
         // 4b. stage B: exact extension of the survivors (seed_filter.cu:762-774)
+        if (D.mask) { // the duplicate table of stage B (cleared here, behind the filter kernel: its phase timer is the kernel's)
+            CU(cudaMemsetAsync(w->d_dedup, 0xFF, (size_t)kDedupSlots * 16, st), SA_ERR_MEMCPY);
+            CU(cudaMemsetAsync(D.tagbits, 0, (size_t)kDedupSlots * 4, st), SA_ERR_MEMCPY);
+        }
         // (a call with more than merge_min survivors is declined here and replayed on the representatives
         // of the merge pass, see below; only the fused path, whose calls are one dedupe scope pair)
         const SurvRec *sv = merged ? w->d_surv_m : w->d_surv;
