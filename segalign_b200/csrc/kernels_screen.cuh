@@ -217,6 +217,8 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     uint32_t key_base = 0, g_total = 0, g_done = 0, g_row_base = 0;
     uint32_t v_cur = 0, v_next = n_var, valid_mask = 0; // device seeding: variant of the current set, lanes with a valid position
     uint32_t lane_kmer = 0;        // lane: exact k-mer of its query position (device seeding)
+    uint32_t pf_v = 0xFFFFFFFFu, pf_end = 0, pf_start = 0; // lane: index entries requested ahead for variant pf_v of the current positions
+    uint32_t cur_end = 0, cur_start = 0;                   // lane: index entries of the set being staged
     bool lane_valid = false;
     uint32_t head = 0, tail = 0;   // hit ring: [head, tail) staged and not yet screened (monotonic counters)
     uint32_t next_c = 0;           // lane 0: the next group number, fetched one refill ahead
@@ -337,10 +339,34 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     qa = (uint32_t)word + H.seed_size;
                 }
             } else if (lane_valid) {
-                const uint32_t kmer = v_cur ? lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur - 1])) : lane_kmer; // seeder.cpp:64-71
-                const uint32_t b_end = __ldg(H.index_table + kmer);
-                b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                // The two index entries of this lane's seed word.  They are random 4-byte reads of a 64 MiB table whose
+                // result the very next instruction needs (ncu: 6.8 % of the kernel's stall samples sat on that
+                // subtraction), so the entries of the NEXT variant of the same 32 positions are requested here and
+                // used one bucket set later; a set staged in several parts keeps its own entries in registers.
+                uint32_t b_end;
+                if (new_set) {
+                    if (pf_v == v_cur) { b_end = pf_end; b_start = pf_start; }
+                    else {
+                        const uint32_t kmer = v_cur ? lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur - 1])) : lane_kmer; // seeder.cpp:64-71
+                        b_end = __ldg(H.index_table + kmer);
+                        b_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                    }
+                    cur_end = b_end; cur_start = b_start;
+                } else {
+                    b_end = cur_end; b_start = cur_start;
+                }
                 n = b_end - b_start;
+            }
+            if (SRC == SRC_RANGE && new_set) {
+                pf_v = 0xFFFFFFFFu;
+                if (v_cur + 1u < n_var) {
+                    pf_v = v_cur + 1u;
+                    if (lane_valid) {
+                        const uint32_t kmer = lane_kmer ^ (2u << (2 * H.shape.tvar[v_cur])); // variant v_cur + 1
+                        pf_end = __ldg(H.index_table + kmer);
+                        pf_start = kmer > 0 ? __ldg(H.index_table + kmer - 1) : 0u;
+                    }
+                }
             }
             uint32_t incl = n;
 #pragma unroll
