@@ -320,7 +320,20 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     if (!valid_mask) continue;
                 }
             }
-            if (SRC == SRC_RANGE && new_set) v_cur = v_next++;
+            if (SRC == SRC_RANGE && new_set) {
+                v_cur = v_next++;
+                // The query records of the NEXT group of 32 positions (its number arrived long ago: it was fetched one
+                // refill ahead) are pulled into L1 while this group's variants are expanded: a new group otherwise
+                // starts with eight lanes' worth of exposed record loads (ncu: 3.3 % of the stall samples at a 500 Mb
+                // block, where a group is 30 rounds; a 100 Mb block has five times as many groups per hit).
+                if (v_cur == 1u) {
+                    const unsigned long long nstart = (unsigned long long)__shfl_sync(0xFFFFFFFFu, next_c, 0) * 32u;
+                    if (nstart < n_units && lane < 8u) {
+                        const uint4 *nq = P.qrec + (int)((H.j0 + (uint32_t)nstart + H.seed_size) >> 5) - 3 + (int)lane;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nq));
+                    }
+                }
+            }
             // this lane's bucket of the set (recomputed when a set is staged in several parts)
             uint32_t b_start = 0, n = 0, qa = 0;
             bool valid = false;
