@@ -149,6 +149,11 @@ __device__ __forceinline__ void cp_async4_hint_s(uint32_t smem_dst, const void *
 __device__ __forceinline__ void sts_v2(uint32_t a, uint32_t x, uint32_t y) {
     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
 }
+// predicated form: no branch (and no convergence barrier pair) around the copy
+__device__ __forceinline__ void cp_async16_s_if(uint32_t smem_dst, const void *gmem_src, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(smem_dst), "l"(gmem_src), "r"((uint32_t)ok) : "memory");
+}
 __device__ __forceinline__ void cp_async16_s(uint32_t smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
@@ -248,20 +253,20 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
     // of the hit's 64-byte row: writes (two rows per quarter warp) and the owners' reads (same chunk of
     // eight rows) are both bank-conflict free without padding.
     auto request_records = [&](uint32_t r_own, uint32_t n) {
+        const uint32_t w1_own = (r_own >> 5) + 1u; // = (w - 3) + REC_FRONT of this lane's own hit
+        const uint32_t rc = lane & 3u, h0 = lane >> 2;
+        // hit h = 8 i + h0 in iteration i: (h >> 1) & 3 = (lane >> 3) & 3 for every i
+        const uint32_t dst0 = sa_stage + (h0 * SCR_STAGE_STRIDE + (rc ^ ((lane >> 3) & 3u))) * 16u;
 #pragma unroll
         for (uint32_t i = 0; i < 4; i++) {
-            const uint32_t hs = i * 8u + (lane >> 2), rc = lane & 3u;
-            const uint32_t r = __shfl_sync(0xFFFFFFFFu, r_own, hs);
-            const uint32_t w1 = (r >> 5) + 1u; // = (w - 3) + REC_FRONT
-            if (hs < n && (rc < 3u || (w1 & 1u))) {
-                const uint64_t *src = rp2_m4 + ((w1 & ~1u) + 2u * rc);
-                const uint32_t dst = sa_stage + (hs * SCR_STAGE_STRIDE + (rc ^ ((hs >> 1) & 3u))) * 16u;
-                // no L2 policy operand here: with `.L2::cache_hint` ptxas 12.9 emits, for the three copies whose
-                // shared address is the first one's plus an immediate, an LDGSTS form that reads an unset uniform
-                // register pair as descriptor (cuobjdump: `[R41+UR0+0x200], desc[UR1]`) -- the launch dies with
-                // "illegal instruction".  The hint bought nothing measurable.
-                cp_async16_s(dst, src);
-            }
+            const uint32_t hs = i * 8u + h0;
+            const uint32_t w1 = __shfl_sync(0xFFFFFFFFu, w1_own, hs);
+            const uint64_t *src = rp2_m4 + ((w1 & ~1u) + 2u * rc);
+            // no L2 policy operand here: with `.L2::cache_hint` ptxas 12.9 emits, for the three copies whose
+            // shared address is the first one's plus an immediate, an LDGSTS form that reads an unset uniform
+            // register pair as descriptor (cuobjdump: `[R41+UR0+0x200], desc[UR1]`) -- the launch dies with
+            // "illegal instruction".  The hint bought nothing measurable.
+            cp_async16_s_if(dst0 + i * (8u * SCR_STAGE_STRIDE * 16u), src, hs < n && (rc < 3u || (w1 & 1u)));
         }
     };
 
@@ -320,20 +325,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                     if (!valid_mask) continue;
                 }
             }
-            if (SRC == SRC_RANGE && new_set) {
-                v_cur = v_next++;
-                // The query records of the NEXT group of 32 positions (its number arrived long ago: it was fetched one
-                // refill ahead) are pulled into L1 while this group's variants are expanded: a new group otherwise
-                // starts with eight lanes' worth of exposed record loads (ncu: 3.3 % of the stall samples at a 500 Mb
-                // block, where a group is 30 rounds; a 100 Mb block has five times as many groups per hit).
-                if (v_cur == 1u) {
-                    const unsigned long long nstart = (unsigned long long)__shfl_sync(0xFFFFFFFFu, next_c, 0) * 32u;
-                    if (nstart < n_units && lane < 8u) {
-                        const uint4 *nq = P.qrec + (int)((H.j0 + (uint32_t)nstart + H.seed_size) >> 5) - 3 + (int)lane;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(nq));
-                    }
-                }
-            }
+            if (SRC == SRC_RANGE && new_set) v_cur = v_next++;
             // this lane's bucket of the set (recomputed when a set is staged in several parts)
             uint32_t b_start = 0, n = 0, qa = 0;
             bool valid = false;

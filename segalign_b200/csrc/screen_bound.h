@@ -52,6 +52,8 @@ struct ScreenConsts {
     uint32_t wlo;  // int8 x3: lower class scores
     int xdrop;
     int hspthresh;
+    int kc1;       // 1 - 65536: packs the match count into the class-count word.  A kernel parameter (constant bank /
+                   // uniform register operand): as a literal ptxas re-materialises it in a register for every block
 };
 
 struct ScreenRec { // = uint4 {p2 lo, p2 hi, terminator bits, soft bits} of 32 cells
@@ -148,7 +150,7 @@ SA_HD int screen_walk(const uint32_t *r, const uint32_t *q, const ScreenConsts &
         const uint32_t tt = (t & ~x) & 0x55555555u; // codes differ by 2: A<->G, C<->T
         const int m = scr_popc(mm), s = scr_popc(tt);
         // class counts as bytes {m, s, 16-m-s, 0}
-        const uint32_t cnt = (uint32_t)(m * (1 - 65536) + s * (256 - 65536) + (16 << 16));
+        const uint32_t cnt = (uint32_t)(m * C.kc1 + s * (256 - 65536) + (16 << 16));
         const int cand = phi + C.amax * m;
         mhat = cand > mhat ? cand : mhat;
         phi = scr_dp4a(cnt, C.whi, phi);
@@ -200,6 +202,7 @@ static inline ScreenConsts screen_consts_from_matrix(const int *sub_mat, int xdr
         }
     C.xdrop = xdrop;
     C.hspthresh = hspthresh;
+    C.kc1 = 1 - 65536;
     return C;
 }
 
