@@ -140,6 +140,17 @@ __device__ __forceinline__ uint32_t lds_b8(uint32_t a) {
 __device__ __forceinline__ void sts_b16(uint32_t a, uint32_t x) {
     asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)x) : "memory");
 }
+__device__ __forceinline__ void sts_b16_if(uint32_t a, uint32_t x, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}" ::"r"(a), "h"((uint16_t)x), "r"((uint32_t)ok) : "memory");
+}
+__device__ __forceinline__ void cp_async4_s_if(uint32_t smem_dst, const void *gmem_src, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
+                 ::"r"(smem_dst), "l"(gmem_src), "r"((uint32_t)ok) : "memory");
+}
+__device__ __forceinline__ void cp_async4_hint_s_if(uint32_t smem_dst, const void *gmem_src, uint64_t policy, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;\n\t}"
+                 ::"r"(smem_dst), "l"(gmem_src), "l"(policy), "r"((uint32_t)ok) : "memory");
+}
 __device__ __forceinline__ void cp_async4_s(uint32_t smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
@@ -428,15 +439,17 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
                 const uint32_t bp = incl - f0 - 1u;
                 const uint32_t bounds = __reduce_or_sync(0xFFFFFFFFu, (n > 0 && incl > f0 && bp < 32u) ? 1u << bp : 0u);
                 const uint32_t j = j0 + __popc(bounds & lt_mask);
-                if (kk * 32u + lane < cnt) {
+                {   // branch-free: lanes past the last hit of the set run the same instructions with the copy and
+                    // the store predicated off (j <= 32 keeps the table reads inside the warp's slice)
+                    const bool ok = kk * 32u + lane < cnt;
                     const uint32_t slot = (tail + kk * 32u + lane) & (uint32_t)(SCR_RING - 1);
                     const uint32_t od = lds_b32(sa_delta + j * 4u), orow = lds_b8(sa_delta + 128u + j);
 #if SA_SCR_L2_HINTS
-                    cp_async4_hint_s(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane), pol_stream);
+                    cp_async4_hint_s_if(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane), pol_stream, ok);
 #else
-                    cp_async4_s(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane));
+                    cp_async4_s_if(sa_ring + slot * 4u, H.pos_table + (od + f0 + lane), ok);
 #endif
-                    sts_b16(sa_meta + slot * 2u, orow | vtag);
+                    sts_b16_if(sa_meta + slot * 2u, orow | vtag, ok);
                 }
             }
             __syncwarp();
@@ -493,7 +506,7 @@ k_filter_hits3(FilterParams P, ScreenConsts C, HitSource H, const int *__restric
             pre_n = pre_next;
             r_next = lane < pre_n ? r_nn + H.seed_size : 0u;
             if (P.ref_has_soft) soft_next = lane < pre_n && soft_window(P.rsoft, r_next);
-            if (pre_n) request_records(r_next, pre_n);
+            request_records(r_next, pre_n); // (pre_n == 0: every copy predicated off)
             cp_async_commit(); // group "R": the records of the next round
             const uint32_t qrow = sa_rows + (rowid & (uint32_t)(SCR_ROWS - 1)) * (SCR_ROW_STRIDE * 4u);
             const uint4 q_a = lds_v4(qrow), q_b = lds_v4(qrow + 16u), q_c = lds_v4(qrow + 32u);
