@@ -189,6 +189,8 @@ typedef struct sa_pipeline_config {
 typedef struct sa_pipeline_report {
     uint64_t ref_blocks, query_blocks, intervals, calls, seeds, hits, hsps, segment_files;
     double seconds;
+    /* wall milliseconds summed over the run's block-level calls (all GPUs of the pool work concurrently) */
+    double ms_ref_upload, ms_table_build, ms_query_upload;
 } sa_pipeline_report;
 int sa_pipeline_run(const sa_pipeline_config *cfg, sa_pipeline_report *report);
 /* The host-only part of sa_pipeline_run: inputs -> blocks -> intervals, block name files, and

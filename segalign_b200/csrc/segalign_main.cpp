@@ -82,10 +82,12 @@ int main(int argc, char **argv) {
         return -rc; // the reference's exit codes (scripts/run_segalign:3-13)
     }
     fprintf(stderr, "ref blocks %llu, query blocks %llu, intervals %llu, SeedAndFilter calls %llu, seeds %llu, hits %llu, "
-                    "HSPs %llu, segment files %llu, %.2f s\n",
+                    "HSPs %llu, segment files %llu, %.2f s (reference blocks: upload + encode %.1f ms, seed position tables %.1f ms; "
+                    "query blocks: upload + encode %.1f ms)\n",
             (unsigned long long)rep.ref_blocks, (unsigned long long)rep.query_blocks, (unsigned long long)rep.intervals,
             (unsigned long long)rep.calls, (unsigned long long)rep.seeds, (unsigned long long)rep.hits,
-            (unsigned long long)rep.hsps, (unsigned long long)rep.segment_files, rep.seconds);
+            (unsigned long long)rep.hsps, (unsigned long long)rep.segment_files, rep.seconds, rep.ms_ref_upload,
+            rep.ms_table_build, rep.ms_query_upload);
     (void)debug; (void)markend;
     return 0;
 }
