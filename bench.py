@@ -61,7 +61,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-from segalign_b200 import genome  # noqa: E402
+from segalign_b200 import genome, sharding  # noqa: E402
 
 SEED_SHAPE = "12of19"
 XDROP, HSPTHRESH = 910, 3000
@@ -273,12 +273,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    wl = Workload(args, rank)
+    strong = bool(args.strong) and world > 1
+    wl = Workload(args, 0 if strong else rank)
     ref, query = wl.ref, wl.query
     nthreads = host_threads(args, world, n_local)
     be = Backend()
     span, setup_ms = setup_backend(be, args, wl, max(2, (nthreads + n_local - 1) // n_local), n_local, first_device=local)
-    units = genome.chunk_list(query.size, span, "both")
+    all_units = genome.chunk_list(query.size, span, "both")
+    # --strong under torchrun: every rank holds the SAME query block and owns a static, contiguous share of
+    # its SeedAndFilter calls (segalign_b200/sharding.py); the calls are independent, so the union of the
+    # ranks' outputs is the single-GPU output (checked below against rank 0 running every call).
+    unit_ids = list(sharding.shard_units(len(all_units), rank, world)) if strong else list(range(len(all_units)))
+    units = [all_units[i] for i in unit_ids]
     q_rc_ascii = genome.revcomp_ascii(query)
     query_bases = int(query.size)
 
@@ -312,7 +318,7 @@ def run_ours(args):
         def work(u):
             rev, j0, j1 = units[u]
             res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
-            crcs[u] = unit_crc(u, res)
+            crcs[u] = unit_crc(unit_ids[u], res)
             return res.size - 1
         n = sum(pool.map(work, range(len(units))))
         step_crc["resident"] = sum(crcs) & 0xFFFFFFFFFFFFFFFF
@@ -344,7 +350,7 @@ def run_ours(args):
             finally:
                 with buf_lock:
                     free_bufs.append(b)
-            crcs[u] = unit_crc(u, res)
+            crcs[u] = unit_crc(unit_ids[u], res)
             with buf_lock:
                 h2d[0] += seeds.size * 8
                 d2h[0] += res.size * 16
@@ -371,7 +377,7 @@ def run_ours(args):
         def work(u):
             rev, j0, j1 = units[u]
             res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
-            crcs[u] = unit_crc(u, res)
+            crcs[u] = unit_crc(unit_ids[u], res)
             with buf_lock:
                 d2h[0] += res.size * 16
             return res.size - 1
@@ -416,9 +422,26 @@ def run_ours(args):
     assert step_crc["resident"] == step_crc["vector_abi"] == step_crc["e2e"], f"legs returned different HSP bytes: {step_crc}"
 
     total_bases = torch.tensor([float(query_bases)], dtype=torch.float64, device="cuda")
-    if world > 1:
+    if world > 1 and not strong:
         dist.all_reduce(total_bases, op=dist.ReduceOp.SUM)
     total_bases = float(total_bases[0])
+    strong_check = None
+    if strong:
+        # union of the ranks' shares == one GPU running every call (same bytes, unit by unit)
+        parts = [None] * world
+        dist.all_gather_object(parts, (step_crc["resident"], hsps_res // args.steps))
+        if rank == 0:
+            crc_all, hsps_all = 0, 0
+            for u, (rev, j0, j1) in enumerate(all_units):
+                res, _ = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
+                crc_all += unit_crc(u, res)
+                hsps_all += res.size - 1
+            crc_all &= 0xFFFFFFFFFFFFFFFF
+            crc_sum = sum(c for c, _ in parts) & 0xFFFFFFFFFFFFFFFF
+            assert crc_sum == crc_all and sum(h for _, h in parts) == hsps_all, \
+                f"sharded ranks returned different HSP bytes than one GPU: {crc_sum:#x} vs {crc_all:#x}"
+            strong_check = {"identical_to_one_gpu": True, "units": len(all_units), "hsps": hsps_all}
+        dist.barrier()
     value = total_bases * args.steps / (ms_res * 1e-3) / 1e9
     e2r_value = total_bases * args.steps / (ms_e2r * 1e-3) / 1e9
     vec_value = total_bases * vsteps / (ms_vec * 1e-3) / 1e9
@@ -495,12 +518,14 @@ def run_ours(args):
 
     if rank == 0:
         par = (f"one process, {n_local} GPUs in the library's pool (replicated ref+table, chunks handed to whichever GPU has a free stream)"
-               if inproc else f"query blocks x{world}, replicated ref+table, no collective")
+               if inproc else
+               f"ONE query block, its SeedAndFilter calls split statically over {world} ranks (sharding.shard_units), replicated ref+table, no collective"
+               if strong else f"query blocks x{world}, replicated ref+table, no collective")
         line = {
             "metric": METRIC, "value": round(value, 5),
             "unit": "Gbp/s", "n_gpus": world * n_local, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_res / args.steps, 3), "higher_is_better": True,
-            "scaling": "strong" if inproc else "weak",
+            "scaling": "strong" if (inproc or strong) else "weak",
             "vs_baseline": None, "dtype": "u8/int32 (f64 entropy factor)", "data": "synthetic",
             "config": {"workload": wl.label, "baseline_config": wl.config_id,
                        "seed": SEED_SHAPE, "transition": True, "xdrop": XDROP, "hspthresh": HSPTHRESH,
@@ -545,6 +570,9 @@ def run_ours(args):
         if inproc:
             line["mode"] = "inproc"
             line["calls_per_gpu"] = gpu_calls_res
+        if strong:
+            line["mode"] = "torchrun-strong"
+            line["sharded_vs_one_gpu"] = strong_check
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -809,6 +837,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syn500", choices=["syn500", "ce11"],
                     help="syn500 = BASELINE configs[2] (default), ce11 = configs[1]")
+    ap.add_argument("--strong", action="store_true",
+                    help="under torchrun: all ranks share ONE query block and split its calls (strong scaling); "
+                         "rank 0 then checks the union against running every call itself")
     ap.add_argument("--inproc", action="store_true", help="one process, --gpus N GPUs in the library's pool (not under torchrun)")
     ap.add_argument("--ref-mb", type=float, default=None, help="scale the reference block (testing only)")
     ap.add_argument("--query-mb", type=float, default=None, help="query block per GPU per step (syn500: default 100)")
