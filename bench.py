@@ -154,6 +154,17 @@ def default_matrix():
     return m.reshape(64)
 
 
+def iupac_matrix():
+    """src/main.cpp:200-203,229-250 with --ambiguous=iupac: N and the other IUPAC letters score 0 against
+    everything below them and against themselves."""
+    m = default_matrix().reshape(8, 8).copy()
+    m[5, :5] = m[:5, 5] = 0
+    m[5, 5] = 0
+    m[6, :6] = m[:6, 6] = 0
+    m[6, 6] = 0
+    return m.reshape(64)
+
+
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -591,6 +602,10 @@ ORACLE_RUNNER = ROOT / "oracle" / "_ref" / "oracle_runner"
 
 
 def reference_gpu_leg(be, wl, span, args):
+    return reference_gpu_compare(be, wl.ref, wl.query, span, args, True, default_matrix(), args.reference_gpu_mb)
+
+
+def reference_gpu_compare(be, ref, query, span, args, transition, matrix, slice_mb):
     """SURVEY 8d "reference GPU timing" / BASELINE.md B1 on the bench workload: oracle_runner (the
     reference's unmodified kernels, sm_100a build) and this backend run the same SeedAndFilter calls
     -- the full reference block, a `--reference-gpu-mb` slice of the bench query as the query block;
@@ -599,18 +614,18 @@ def reference_gpu_leg(be, wl, span, args):
     from tests import harness as H   # file formats + record comparison only; nothing of oracle/ is imported
     if not ORACLE_RUNNER.exists():
         return {"unavailable": "oracle/_ref/oracle_runner not built (needs /root/reference at build time)"}
-    qn = int(min(wl.query.size, args.reference_gpu_mb * 1e6))
-    q = np.ascontiguousarray(wl.query[:qn])
+    qn = int(min(query.size, slice_mb * 1e6))
+    q = np.ascontiguousarray(query[:qn])
     work = Path(tempfile.mkdtemp(prefix="sa_refgpu_"))
     try:
         cf, of = work / "slice.case", work / "slice.out"
         with open(cf, "wb") as f:   # SACASE01 (oracle/ref_driver.cpp:read_case), the bench's own parameters
             shape = SEED_SHAPE.encode()
             f.write(b"SACASE01" + struct.pack("<I", len(shape)) + shape)
-            f.write(struct.pack("<iIiiiIIii", 1, 1, XDROP, HSPTHRESH, 0, genome.DEFAULT_WGA_CHUNK,
+            f.write(struct.pack("<iIiiiIIii", int(bool(transition)), 1, XDROP, HSPTHRESH, 0, genome.DEFAULT_WGA_CHUNK,
                                 genome.DEFAULT_LASTZ_INTERVAL, 0, 0))
-            f.write(default_matrix().astype("<i4").tobytes())
-            f.write(struct.pack("<Q", wl.ref.size)); f.write(wl.ref.tobytes())
+            f.write(np.asarray(matrix).astype("<i4").tobytes())
+            f.write(struct.pack("<Q", ref.size)); f.write(ref.tobytes())
             f.write(struct.pack("<Q", q.size)); f.write(q.tobytes())
         t0 = time.perf_counter()
         p = subprocess.run([str(ORACLE_RUNNER), str(cf), str(of)], stderr=subprocess.PIPE, stdout=subprocess.DEVNULL,
@@ -636,7 +651,7 @@ def reference_gpu_leg(be, wl, span, args):
     got, t_calls = [], 0.0
     for rev, j0, j1 in genome.chunk_list(q.size, span, "both"):
         t1 = time.perf_counter()
-        res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 1)
+        res, ns = be.SeedAndFilterRange(j0, j1, bool(transition), bool(rev), 1)
         t_calls += time.perf_counter() - t1
         if ns:
             got.append((rev, j0, j1, ns, res))
@@ -645,7 +660,7 @@ def reference_gpu_leg(be, wl, span, args):
     ref_s = float(dump.times[4])
     return {"seconds": round(ref_s, 3), "ours_seconds": round(t_calls, 4), "speedup": round(ref_s / max(1e-9, t_calls), 1),
             "identical": True, "calls": len(want), "hits": int(dump.counters[1]), "hsps": int(dump.counters[2]),
-            "query_slice_bp": qn, "ref_bp": int(wl.ref.size),
+            "query_slice_bp": qn, "ref_bp": int(ref.size),
             "gbp_per_s": round(qn / ref_s / 1e9, 6) if ref_s > 0 else None,
             "reference_table_build_s": round(float(dump.times[1]), 3),
             "reference_host_seedgen_s": round(float(dump.times[3]), 3),
@@ -670,7 +685,7 @@ def extra_workloads(be, args, pool, nthreads):
     span = len(shape_pattern(SEED_SHAPE))
     out = {}
 
-    def run(name, ref, query, steps, note, warm=True):
+    def run(name, ref, query, steps, note, warm=True, transition=True):
         be.ClearQuery(0)
         be.ClearRef()
         be.SendRefWriteRequest(ref, 0, ref.size)
@@ -680,7 +695,7 @@ def extra_workloads(be, args, pool, nthreads):
 
         def work(u):
             rev, j0, j1 = units[u]
-            res, ns = be.SeedAndFilterRange(j0, j1, True, bool(rev), 0)
+            res, ns = be.SeedAndFilterRange(j0, j1, transition, bool(rev), 0)
             return res.size - 1
         if warm:
             hs = sum(pool.map(work, range(len(units))))
@@ -708,6 +723,35 @@ def extra_workloads(be, args, pool, nthreads):
         a.workload, a.ref_mb, a.query_mb = "ce11", None, None
         w1 = Workload(a, 0)
         run("configs1_ce11_scale", w1.ref, w1.query, 3, w1.label)
+    if not args.no_chr1:
+        # BASELINE configs[3] (hg38 chr1 vs mm39 chr1, --notransition --ambiguous=iupac) at its block size: one
+        # 248 Mb record, half of it soft-masked, an 18 Mb and forty 50 kb runs of N, IUPAC letters at 1e-5; the query
+        # is a 100 Mb slice of its 40 %-diverged copy with its own masking and N runs.  Other scoring options than
+        # the main legs: the processor is set up again (the last thing this function does).
+        rng = np.random.default_rng(20261018)
+        n = 248_000_000
+        base = genome.random_genome(n, rng)
+        q = genome.mutate(base[60_000_000:160_000_000], 0.40, rng)
+        ref = genome.soft_mask(base, 0.5, rng)
+        ref[122_000_000:140_000_000] = ord("N")
+        ref = genome.insert_runs(ref, b"N", 40, 50_000, rng)
+        ref = genome.sprinkle(ref, b"RYKMSWN", 1e-5, rng)
+        q = genome.soft_mask(q, 0.4, rng)
+        q = genome.insert_runs(q, b"N", 20, 50_000, rng)
+        q = genome.sprinkle(q, b"RYKMSWN", 1e-5, rng)
+        be.ShutdownProcessor()
+        be.InitializeInterface(1, first_device=int(os.environ.get("LOCAL_RANK", "0")))
+        be.GenerateShapePos(SEED_SHAPE)
+        be.InitializeProcessor(False, genome.DEFAULT_WGA_CHUNK, span, iupac_matrix(), XDROP, HSPTHRESH, False)
+        run("configs3_chr1_scale_notransition_iupac", ref, q, 3,
+            "BASELINE configs[3] flags at chr1 scale, synthetic: 248 Mb reference record (50 % soft-masked, 18 Mb + 40 x 50 kb "
+            "of N, IUPAC letters) x 100 Mb query slice (40 % diverged), --notransition --ambiguous=iupac; 1 GPU",
+            transition=False)
+        if not args.no_reference_gpu:
+            r = reference_gpu_compare(be, ref, q, span, args, False, iupac_matrix(), args.reference_gpu_mb)
+            out["configs3_chr1_scale_notransition_iupac"]["reference_gpu"] = {
+                k: r[k] for k in ("seconds", "ours_seconds", "speedup", "identical", "calls", "hits", "hsps",
+                                  "query_slice_bp", "unavailable") if k in r}
     return out
 
 
@@ -837,6 +881,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syn500", choices=["syn500", "ce11"],
                     help="syn500 = BASELINE configs[2] (default), ce11 = configs[1]")
+    ap.add_argument("--no-chr1", action="store_true", help="skip the configs[3]-scale secondary workload")
     ap.add_argument("--strong", action="store_true",
                     help="under torchrun: all ranks share ONE query block and split its calls (strong scaling); "
                          "rank 0 then checks the union against running every call itself")
