@@ -97,3 +97,21 @@ def test_shard_intervals_round_robin():
     parts = [sharding.shard_intervals(iv, r, 4) for r in range(4)]
     assert sorted(x for p in parts for x in p) == iv
     assert [len(p) for p in parts] == [3, 3, 2, 2]
+
+
+def test_bench_matrices_match_the_reference_construction():
+    """bench.py restates src/main.cpp:187-268 for its own runs (it may not import the oracle on the product
+    legs); both matrices must equal the checker's."""
+    import bench
+    from oracle import sa_oracle_py as sao
+    assert np.array_equal(np.asarray(sao.build_matrix("", bench.XDROP)).reshape(64), bench.default_matrix())
+    assert np.array_equal(np.asarray(sao.build_matrix("iupac", bench.XDROP)).reshape(64), bench.iupac_matrix())
+
+
+def test_strong_sharding_covers_every_call_once():
+    """bench.py --strong: the ranks' static shares of one query block's SeedAndFilter calls."""
+    from segalign_b200 import sharding
+    units = genome.chunk_list(100_000_000, 19, "both")
+    for world in (2, 3, 8):
+        got = [u for r in range(world) for u in sharding.shard_units(len(units), r, world)]
+        assert got == list(range(len(units)))
