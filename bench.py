@@ -680,6 +680,25 @@ def reference_gpu_compare(be, ref, query, span, args, transition, matrix, slice_
 
 
 # ------------------------------------------------------------------------------ secondary workloads (not the headline)
+def make_chr1_pair(n=248_000_000, query_lo=60_000_000, query_n=100_000_000, seed=20261018):
+    """configs[3]-scale synthetic pair: one reference record (half soft-masked, an 18 Mb and forty 50 kb runs of N,
+    IUPAC letters at 1e-5) and a slice of its 40 %-diverged copy with its own masking and N runs."""
+    rng = np.random.default_rng(seed)
+    base = genome.random_genome(n, rng)
+    q = genome.mutate(base[query_lo:query_lo + query_n], 0.40, rng)
+    ref = genome.soft_mask(base, 0.5, rng)
+    ref[n // 2 - n // 28:n // 2 + n // 28] = ord("N")
+    ref = genome.insert_runs(ref, b"N", 40, 50_000, rng)
+    ref = genome.sprinkle(ref, b"RYKMSWN", 1e-5, rng)
+    q = genome.soft_mask(q, 0.4, rng)
+    q = genome.insert_runs(q, b"N", 20, 50_000, rng)
+    # N only in the query: the reference's host RevComp (common/ntcoding.cpp:63-105) silently drops every other
+    # IUPAC letter, which shifts its minus-strand seeds against its own device-side reverse complement -- outside
+    # defined behaviour, so not a parity input (tests/harness.py keeps such queries to the plus strand)
+    q = genome.sprinkle(q, b"N", 1e-5, rng)
+    return ref, q
+
+
 def extra_workloads(be, args, pool, nthreads):
     """BASELINE configs[0] (E. coli-size self-alignment and its 40 %-diverged variant) and configs[1]
     (the round-1 headline) through the resident leg, a few steps each."""
@@ -731,20 +750,7 @@ def extra_workloads(be, args, pool, nthreads):
         # 248 Mb record, half of it soft-masked, an 18 Mb and forty 50 kb runs of N, IUPAC letters at 1e-5; the query
         # is a 100 Mb slice of its 40 %-diverged copy with its own masking and N runs.  Other scoring options than
         # the main legs: the processor is set up again (the last thing this function does).
-        rng = np.random.default_rng(20261018)
-        n = 248_000_000
-        base = genome.random_genome(n, rng)
-        q = genome.mutate(base[60_000_000:160_000_000], 0.40, rng)
-        ref = genome.soft_mask(base, 0.5, rng)
-        ref[122_000_000:140_000_000] = ord("N")
-        ref = genome.insert_runs(ref, b"N", 40, 50_000, rng)
-        ref = genome.sprinkle(ref, b"RYKMSWN", 1e-5, rng)
-        q = genome.soft_mask(q, 0.4, rng)
-        q = genome.insert_runs(q, b"N", 20, 50_000, rng)
-        # N only in the query: the reference's host RevComp (common/ntcoding.cpp:63-105) silently drops every other
-        # IUPAC letter, which shifts its minus-strand seeds against its own device-side reverse complement -- outside
-        # defined behaviour, so not a parity input (tests/harness.py keeps such queries to the plus strand)
-        q = genome.sprinkle(q, b"N", 1e-5, rng)
+        ref, q = make_chr1_pair()
         be.ShutdownProcessor()
         be.InitializeInterface(1, first_device=int(os.environ.get("LOCAL_RANK", "0")))
         be.GenerateShapePos(SEED_SHAPE)

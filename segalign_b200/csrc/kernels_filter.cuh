@@ -14,13 +14,15 @@
 //   * cells are scored with the true sub_mat values of the ACGT x ACGT block (int8 LUT);
 //   * the walk stops only (a) at a cell that is > xdrop below a maximum seen BEFORE its 4-cell
 //     group started -- the reference's own rule would have stopped there or earlier -- or (b) at a
-//     "terminator" cell: a non-ACGT code whose every matrix entry is < -xdrop, where the
-//     reference's rule always fires, or a cell past the end of a block (those score 0 and can
-//     never raise the maximum, :332-336,:420);
+//     "terminator" cell: a non-ACGT code whose matrix entries against every code that is not
+//     "soft" are < -xdrop (screen_bound.h: screen_terminator_codes), where the reference's rule
+//     always fires unless the opposite cell is soft, or a cell past the end of a block (those
+//     score 0 and can never raise the maximum, :332-336,:420);
 //   * M is raised by every cell of every visited group, including cells the reference would no
 //     longer visit (over-estimate only);
 //   * a non-ACGT cell that is not a terminator (code X under the default matrix, N/X under
-//     --ambiguous) inside the walked range makes the hit a survivor outright.
+//     --ambiguous) inside the walked range, the stopping cell included, makes the hit a survivor
+//     outright.
 //
 // Execution model: "persistent lanes".  Each lane owns one hit at a time and advances it by one
 // 32-cell tile per loop trip; a lane whose hit is finished takes the next hit from a warp-level
@@ -206,7 +208,9 @@ __device__ __forceinline__ void tile_walk(uint32_t lut_lane, uint32_t mul, uint3
         m1 = 0x01000000u; m2 = 0x01010000u; m3 = 0x01010100u;
     }
     const int n_eff = __clz(__brev(T));          // cells before the first terminator (32 if none)
-    const uint32_t valid = n_eff >= 32 ? 0xFFFFFFFFu : ((1u << n_eff) - 1u);
+    // a soft cell in front of the first terminator cell, or AT it: a terminator code only stops the walk against a
+    // cell that is not soft (screen_terminator_codes: lower case x N scores 0 under --ambiguous)
+    const uint32_t valid = n_eff >= 31 ? 0xFFFFFFFFu : ((2u << n_eff) - 1u);
     survive = (S & valid) != 0;
     const int ng = survive ? 0 : (n_eff + 3) >> 2; // groups to visit (the last may run past the terminator)
     bool dropped = false;

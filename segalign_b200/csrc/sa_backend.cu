@@ -141,7 +141,8 @@ struct Global {
     uint32_t max_seeds = 0, max_hits = 0, max_hits_device = 0, seed_size = 0;
     int sub_mat[64] = {};
     int xdrop = 0, hspthresh = 0, noentropy = 0, diag_all_positive = 0, transition = 0;
-    uint32_t term_codes = 0;   // non-ACGT codes that always trip the X-drop rule (kernels_filter.cuh)
+    uint32_t term_codes = 0;   // non-ACGT codes the filter stage treats as X-drop terminators (screen_terminator_codes)
+    uint32_t strict_term_codes = 0; // ... those that trip the X-drop rule against every code
     bool filter_ok = false;    // ACGT x ACGT scores fit int8: the filter stage is usable
     bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
@@ -496,7 +497,7 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.xdrop = G.xdrop; P.hspthresh = G.hspthresh; P.noentropy = G.noentropy;
     P.diag_all_positive = G.diag_all_positive;
     P.scores_fit_int8 = G.filter_ok;
-    P.soft_runs = (((G.term_codes >> L_NT) & 1u) == 0 || ((G.term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
+    P.soft_runs = (((G.strict_term_codes >> L_NT) & 1u) == 0 || ((G.strict_term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
     P.win_lo = in.win_lo; P.win_hi = in.win_hi;
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
@@ -835,21 +836,15 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     G.noentropy = noentropy;
     memcpy(G.sub_mat, sub_mat, sizeof(G.sub_mat));
     G.diag_all_positive = sub_mat[0] > 0 && sub_mat[9] > 0 && sub_mat[18] > 0 && sub_mat[27] > 0;
-    // kernels_filter.cuh preconditions: int8 ACGT block; terminator codes = non-ACGT codes whose
-    // every entry is < -xdrop (the reference's X-drop rule then always fires on that cell)
+    // kernels_filter.cuh preconditions: int8 ACGT block; terminator / soft classes of the non-ACGT codes
+    // (screen_bound.h: screen_terminator_codes)
     G.filter_ok = true;
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++)
             if (sub_mat[a * 8 + b] < -128 || sub_mat[a * 8 + b] > 127) G.filter_ok = false;
     G.screen = screen_consts_from_matrix(sub_mat, xdrop, hspthresh);
     if (!G.filter_ok) G.screen.enabled = 0;
-    G.term_codes = 0;
-    for (int c = 4; c < 8; c++) {
-        bool term = true;
-        for (int d = 0; d < 8; d++)
-            if (sub_mat[c * 8 + d] >= -xdrop || sub_mat[d * 8 + c] >= -xdrop) term = false;
-        if (term) G.term_codes |= 1u << c;
-    }
+    G.term_codes = screen_terminator_codes(sub_mat, xdrop, &G.strict_term_codes);
     const char *fenv = getenv("SEGALIGN_B200_FILTER");
     G.use_filter = !(fenv && atoi(fenv) == 0);
     const char *denv = getenv("SEGALIGN_B200_DEDUP");

@@ -206,4 +206,38 @@ static inline ScreenConsts screen_consts_from_matrix(const int *sub_mat, int xdr
     return C;
 }
 
+// Which non-ACGT codes (4..7) the filter stage may treat as X-drop terminators; every other non-ACGT code is
+// "soft".  The two classes are defined together:
+//   * a hit with a soft cell anywhere in its examined range is never decided by the filter (screen: soft flag of
+//     either window; tile walk: a soft cell at or before the first terminator cell makes the hit a survivor);
+//   * so a terminator code only has to stop the reference's walk when the cell it is paired with is NOT soft:
+//     code c is a terminator iff sub_mat[c][d] < -xdrop and sub_mat[d][c] < -xdrop for every d that is A/C/G/T or
+//     itself a terminator (the running sum then falls more than xdrop below the running maximum at that cell).
+// The strict rule "every entry of the code's row and column < -xdrop" (round 1) is the special case without soft
+// codes.  It made lower case a soft code under --ambiguous=n|iupac (lower case x N scores 0 there although lower case
+// x ACGT is -1000), and on a half soft-masked block nearly every hit then went to the tile walk.
+// `strict` (optional): the codes that are terminators against everything.
+static inline uint32_t screen_terminator_codes(const int *sub_mat, int xdrop, uint32_t *strict = nullptr) {
+    uint32_t soft = 0, all = 0;
+    for (int c = 4; c < 8; c++) {
+        bool every = true;
+        for (int d = 0; d < 8; d++) {
+            const bool high = sub_mat[c * 8 + d] >= -xdrop || sub_mat[d * 8 + c] >= -xdrop;
+            if (high) every = false;
+            if (high && d < 4) soft |= 1u << c;
+        }
+        if (every) all |= 1u << c;
+    }
+    for (bool changed = true; changed;) { // two remaining candidates that do not stop each other: both soft
+        changed = false;
+        for (int c = 4; c < 8; c++)
+            for (int d = 4; d < 8; d++) {
+                if (((soft >> c) | (soft >> d)) & 1u) continue;
+                if (sub_mat[c * 8 + d] >= -xdrop || sub_mat[d * 8 + c] >= -xdrop) { soft |= (1u << c) | (1u << d); changed = true; }
+            }
+    }
+    if (strict) *strict = all;
+    return ~soft & 0xF0u;
+}
+
 } // namespace sa

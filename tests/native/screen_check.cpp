@@ -108,13 +108,7 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> rb(RL), qb(QL);
     sao_encode(ref.data(), (uint32_t)RL, rb.data());
     sao_encode(qry.data(), (uint32_t)QL, qb.data());
-    uint32_t term_codes = 0;
-    for (int c = 4; c < 8; c++) { // sa_initialize_processor
-        bool term = true;
-        for (int d = 0; d < 8; d++)
-            if (P.sub_mat[c * 8 + d] >= -xdrop || P.sub_mat[d * 8 + c] >= -xdrop) term = false;
-        if (term) term_codes |= 1u << c;
-    }
+    const uint32_t term_codes = screen_terminator_codes(P.sub_mat, xdrop); // as sa_initialize_processor
     const Records RR = pack(rb, term_codes), QR = pack(qb, term_codes);
     const ScreenConsts C = screen_consts_from_matrix(P.sub_mat, xdrop, thresh);
     if (!C.enabled) { printf("screen disabled for this matrix\n"); return 0; }

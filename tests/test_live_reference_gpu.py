@@ -63,6 +63,21 @@ def gen_chr1_like(rng):
     return ref, q[:4_000_000]
 
 
+def gen_masked_x_ambiguous(rng, n=400_000):
+    """Lower case opposite N, N opposite lower case, lower case opposite lower case -- inside homologous sequence.
+    Under --ambiguous=n|iupac the first two pairs score 0 and HSPs run through them, the third is -1000 and stops
+    them: lower case is a terminator code for the filter stage only while the opposite cell is not N
+    (screen_bound.h: screen_terminator_codes; kernels_filter.cuh: tile_walk's inclusive soft test)."""
+    ref = genome.random_genome(n, rng)
+    q = genome.mutate(ref, 0.15, rng)
+    sites = rng.permutation(n - 2)[:n // 40]
+    a, b, c = np.array_split(sites, 3)
+    ref[a] |= 0x20; q[a] = ord("N")
+    ref[b] = ord("N"); q[b] |= 0x20
+    ref[c] |= 0x20; q[c] |= 0x20
+    return ref, q
+
+
 def gen_fresh(rng):
     """Everything at once, small: several chromosomes, soft-masking, N runs, inversions, a repeat family."""
     ref, q = H.gen_masked_multichrom(rng, n=400_000, d=0.22, chroms=3, f_mask=0.2)
@@ -72,7 +87,8 @@ def gen_fresh(rng):
 
 
 H.GENERATORS.update(ecoli_self=gen_ecoli_self, ecoli_mut40=gen_ecoli_mut40, worm_piece=gen_worm_piece,
-                    chr1_like=gen_chr1_like, syn500_piece=gen_syn500_piece, fresh=gen_fresh)
+                    chr1_like=gen_chr1_like, syn500_piece=gen_syn500_piece, fresh=gen_fresh,
+                    masked_x_ambiguous=gen_masked_x_ambiguous)
 
 # SEGALIGN_LIVE_FULL=1 (tests/golden/check_large.py sets it) runs the self-alignment at E. coli size:
 # the reference kernels need ~270 s for it on a B200 (every main-diagonal hit re-walks the diagonal).
@@ -86,6 +102,8 @@ LIVE_CASES = [
     H.Case("syn500_piece_100Mb_x_2Mb", "syn500_piece"),        # configs[2] at reduced size
     H.Case("chr1_like_6Mb_x_4Mb_iupac_notransition", "chr1_like", transition=False, ambiguous="iupac",
            strand="plus"),                                    # configs[3] flags at reduced size
+    H.Case("masked_x_ambiguous_iupac", "masked_x_ambiguous", ambiguous="iupac", rng_seed=41),
+    H.Case("masked_x_ambiguous_n_notransition", "masked_x_ambiguous", ambiguous="n", transition=False, rng_seed=42),
     H.Case("fresh_seed", "fresh", rng_seed=FRESH_SEED, wga_chunk=100_000),
 ]
 
