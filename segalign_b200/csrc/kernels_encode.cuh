@@ -111,6 +111,70 @@ __device__ __forceinline__ bool seed_valid(uint32_t mwin, int span) {
 
 // Seed table pass 1 (seed_pos_table.cu:69-81): key/position pairs + bucket histogram.
 // Invalid positions get key 4^w so a radix sort moves them behind every real bucket.
+// b8 -> the zero-run planes of stage B (screen_bound.h: zero_run_codes): f1 / g1 = 1 bit per base, set where the cell's
+// code is flat / a partner; padding words and cells past the end are 0.  counter += number of flat cells.
+__global__ void __launch_bounds__(256)
+k_pack_zero_planes(const uint8_t *__restrict__ b8, uint32_t len, uint32_t *__restrict__ f1, uint32_t *__restrict__ g1,
+                   uint32_t words, uint32_t flat, uint32_t partners, uint32_t *__restrict__ counter) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t nflat = 0;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += stride) {
+        uint32_t f = 0, g = 0;
+        const unsigned long long base = (unsigned long long)w << 5;
+        if (base + 32 <= len) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(b8 + base);
+            const uint4 a = __ldg(p), b = __ldg(p + 1);
+            const uint32_t x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = (x[k] >> (8 * j)) & 7u;
+                    f |= ((flat >> c) & 1u) << (4 * k + j);
+                    g |= ((partners >> c) & 1u) << (4 * k + j);
+                }
+            }
+        } else {
+            for (int cell = 0; cell < 32; cell++) {
+                if (base + cell < len) {
+                    const uint32_t c = b8[base + cell] & 7u;
+                    f |= ((flat >> c) & 1u) << cell;
+                    g |= ((partners >> c) & 1u) << cell;
+                }
+            }
+        }
+        f1[w] = f;
+        g1[w] = g;
+        nflat += __popc(f);
+    }
+    if (nflat) atomicAdd(counter, nflat);
+}
+
+// Coarse level: bit p of F1k / G1k = all 1024 bases of the aligned piece p exist and are flat / partners.  One thread
+// per piece; the 32 pieces of an output word are combined by a ballot.
+__global__ void __launch_bounds__(256)
+k_coarse_zero_planes(const uint32_t *__restrict__ f1, const uint32_t *__restrict__ g1, uint32_t words,
+                     uint32_t *__restrict__ F1k, uint32_t *__restrict__ G1k, uint32_t coarse_words) {
+    const uint32_t pieces = coarse_words * 32u; // a multiple of the warp size: whole warps run the loop together
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pc = blockIdx.x * blockDim.x + threadIdx.x; pc < pieces; pc += stride) {
+        const unsigned long long first = (unsigned long long)pc * 32u;
+        uint32_t af = 0, ag = 0;
+        if (first + 32u <= words) {
+            af = ag = 0xFFFFFFFFu;
+            const uint4 *pf = reinterpret_cast<const uint4 *>(f1 + first), *pg = reinterpret_cast<const uint4 *>(g1 + first);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint4 a = __ldg(pf + k), b = __ldg(pg + k);
+                af &= a.x & a.y & a.z & a.w;
+                ag &= b.x & b.y & b.z & b.w;
+            }
+        }
+        const uint32_t mf = __ballot_sync(0xFFFFFFFFu, af == 0xFFFFFFFFu), mg = __ballot_sync(0xFFFFFFFFu, ag == 0xFFFFFFFFu);
+        if ((threadIdx.x & 31u) == 0) { F1k[pc >> 5] = mf; G1k[pc >> 5] = mg; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_table_keys(const uint64_t *__restrict__ p2, const uint32_t *__restrict__ m1, ShapeDesc sh,
              uint32_t start_offset, uint32_t step, uint32_t num_steps, uint32_t *__restrict__ keys,

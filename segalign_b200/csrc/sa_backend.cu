@@ -143,6 +143,7 @@ struct Global {
     int xdrop = 0, hspthresh = 0, noentropy = 0, diag_all_positive = 0, transition = 0;
     uint32_t term_codes = 0;   // non-ACGT codes the filter stage treats as X-drop terminators (screen_terminator_codes)
     uint32_t strict_term_codes = 0; // ... those that trip the X-drop rule against every code
+    uint32_t zero_flat = 0, zero_partners = 0; // code sets of the zero-run planes (screen_bound.h: zero_run_codes); 0 = none
     bool filter_ok = false;    // ACGT x ACGT scores fit int8: the filter stage is usable
     bool use_filter = true;    // SEGALIGN_B200_FILTER=0 routes every hit to the exact kernel
     bool use_dedup = true;     // SEGALIGN_B200_DEDUP=0 appends every passing record (no duplicate table)
@@ -196,6 +197,7 @@ int free_planes(SeqPlanes &p, cudaStream_t st) {
     if (p.m1) CU(cudaFreeAsync(p.m1, st), SA_ERR_FREE);
     if (p.softmap) CU(cudaFreeAsync(p.softmap, st), SA_ERR_FREE);
     if (p.rec_base) CU(cudaFreeAsync(p.rec_base, st), SA_ERR_FREE);
+    if (p.zr) CU(cudaFreeAsync(p.zr, st), SA_ERR_FREE);
     p = SeqPlanes();
     return SA_OK;
 }
@@ -218,17 +220,44 @@ int alloc_planes(SeqPlanes &p, uint32_t len, const char *tag, cudaStream_t st) {
     return SA_OK;
 }
 
-// filter records of one block under the current terminator set (async on the control stream)
-void build_records(GpuCtx &g, SeqPlanes &p) {
+// filter records of one block under the current terminator set, and its zero-run planes under the current flat /
+// partner code sets (async on the control stream)
+int build_records(GpuCtx &g, SeqPlanes &p) {
     cudaMemsetAsync(p.softmap, 0, ((size_t)p.softmap_words + 1) * sizeof(uint32_t), g.ctrl);
     k_pack_records<<<grid_for(p.words + REC_FRONT, 256), 256, 0, g.ctrl>>>(p.b8, p.len, p.rec, REC_FRONT,
                                                                             (uint32_t)p.words, G.term_codes, p.softmap, p.softmap_words);
     p.term_codes = G.term_codes;
+    p.zero_codes = G.zero_flat | (G.zero_partners << 8);
+    if (G.zero_flat) {
+        p.coarse_words = (uint32_t)(p.words / 1024 + 3);
+        const size_t zw = (p.words + 3) & ~(size_t)3; // plane stride: keeps g1 16-byte aligned
+        const size_t total = 2 * zw + 2 * (size_t)p.coarse_words + 1;
+        if (!p.zr) {
+            cudaError_t e = cudaMallocAsync((void **)&p.zr, total * sizeof(uint32_t), g.ctrl);
+            if (e != cudaSuccess)
+                return fail(SA_ERR_MALLOC, "cudaMalloc of %zu bytes for the zero-run planes failed with error \" %s \"",
+                            total * sizeof(uint32_t), cudaGetErrorString(e));
+        }
+        p.f1 = p.zr; p.g1 = p.f1 + zw; p.F1k = p.g1 + zw; p.G1k = p.F1k + p.coarse_words;
+        uint32_t *counter = p.G1k + p.coarse_words;
+        cudaMemsetAsync(p.F1k, 0, (2 * (size_t)p.coarse_words + 1) * sizeof(uint32_t), g.ctrl);
+        k_pack_zero_planes<<<grid_for(p.words, 256), 256, 0, g.ctrl>>>(p.b8, p.len, p.f1, p.g1, (uint32_t)p.words, G.zero_flat,
+                                                                     G.zero_partners, counter);
+        k_coarse_zero_planes<<<grid_for((size_t)p.coarse_words * 32, 256), 256, 0, g.ctrl>>>(p.f1, p.g1, (uint32_t)p.words, p.F1k, p.G1k,
+                                                                                          p.coarse_words);
+        add_launches(2);
+    } else if (p.zr) {
+        cudaFreeAsync(p.zr, g.ctrl);
+        p.zr = p.f1 = p.g1 = p.F1k = p.G1k = nullptr;
+    }
+    return SA_OK;
 }
-// host copy of the block's soft-record count (after the control stream has been awaited)
+// host copies of the block's soft-record and flat-cell counts (after the control stream has been awaited)
 int read_soft_flag(SeqPlanes &p) {
     p.has_soft = 0;
     if (p.softmap) CU(cudaMemcpy(&p.has_soft, p.softmap + p.softmap_words, sizeof(uint32_t), cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
+    p.has_flat = 0;
+    if (p.zr) CU(cudaMemcpy(&p.has_flat, p.G1k + p.coarse_words, sizeof(uint32_t), cudaMemcpyDeviceToHost), SA_ERR_MEMCPY);
     return SA_OK;
 }
 
@@ -259,8 +288,8 @@ int enqueue_encode(GpuCtx &g, uint32_t len, SeqPlanes &fwd, SeqPlanes *rc, const
     if (rc)
         k_pack_planes<<<grid_for(rc->words, 256), 256, 0, g.ctrl>>>(rc->b8, len, rc->p2, rc->m1,
                                                                      (uint32_t)rc->words);
-    build_records(g, fwd);
-    if (rc) build_records(g, *rc);
+    TRY(build_records(g, fwd));
+    if (rc) TRY(build_records(g, *rc));
     add_launches(rc ? 5 : 3);
     CU(cudaGetLastError(), SA_ERR_KERNEL);
     return SA_OK;
@@ -304,6 +333,7 @@ int upload_block_all_gpus(const char *src, uint32_t len, int slot, const char *t
         CU(cudaSetDevice(G.gpus[i].device), SA_ERR_SET_DEVICE);
         CU(cudaStreamSynchronize(G.gpus[i].ctrl), SA_ERR_KERNEL);
         if (slot < 0) TRY(read_soft_flag(G.gpus[i].ref));
+        else { TRY(read_soft_flag(G.gpus[i].q_fwd[slot])); G.gpus[i].q_rc[slot].has_flat = G.gpus[i].q_fwd[slot].has_flat; }
     }
     return SA_OK;
 }
@@ -499,6 +529,9 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.scores_fit_int8 = G.filter_ok;
     P.soft_runs = (((G.strict_term_codes >> L_NT) & 1u) == 0 || ((G.strict_term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
     P.win_lo = in.win_lo; P.win_hi = in.win_hi;
+    P.zskip = (g.ref.zr && q.zr && (g.ref.has_flat || q.has_flat)) ? 1 : 0;
+    P.rf1 = g.ref.f1; P.rg1 = g.ref.g1; P.rF1k = g.ref.F1k; P.rG1k = g.ref.G1k;
+    P.qf1 = q.f1; P.qg1 = q.g1; P.qF1k = q.F1k; P.qG1k = q.G1k;
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
     F.rp2 = g.ref.p2; F.rsoft = g.ref.softmap; F.ref_has_soft = g.ref.has_soft ? 1 : 0;
@@ -845,6 +878,8 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
     G.screen = screen_consts_from_matrix(sub_mat, xdrop, hspthresh);
     if (!G.filter_ok) G.screen.enabled = 0;
     G.term_codes = screen_terminator_codes(sub_mat, xdrop, &G.strict_term_codes);
+    zero_run_codes(sub_mat, &G.zero_flat, &G.zero_partners);
+    if (const char *e = getenv("SEGALIGN_B200_ZERO_RUNS")) if (atoi(e) == 0) G.zero_flat = G.zero_partners = 0;
     const char *fenv = getenv("SEGALIGN_B200_FILTER");
     G.use_filter = !(fenv && atoi(fenv) == 0);
     const char *denv = getenv("SEGALIGN_B200_DEDUP");
@@ -889,9 +924,10 @@ int sa_initialize_processor(int transition, uint32_t wga_chunk, uint32_t seed_si
         // blocks uploaded before the matrix was known carry records built for another terminator set
         SeqPlanes *all[] = {&g.ref, &g.q_fwd[0], &g.q_rc[0], &g.q_fwd[1], &g.q_rc[1]};
         for (SeqPlanes *p : all)
-            if (p->rec && p->term_codes != G.term_codes) build_records(g, *p);
+            if (p->rec && (p->term_codes != G.term_codes || p->zero_codes != (G.zero_flat | (G.zero_partners << 8)))) TRY(build_records(g, *p));
         CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
-        if (g.ref.rec) TRY(read_soft_flag(g.ref));
+        for (SeqPlanes *p : all)
+            if (p->rec) TRY(read_soft_flag(*p));
         for (int k = 0; k < G.ws_per_gpu; k++) {
             Workspace *w = nullptr;
             TRY(make_workspace((int)i, w));
@@ -1217,6 +1253,8 @@ int sa_rm_send_query(void) {
     for (auto &g : G.gpus) {
         CU(cudaSetDevice(g.device), SA_ERR_SET_DEVICE);
         CU(cudaStreamSynchronize(g.ctrl), SA_ERR_KERNEL);
+        TRY(read_soft_flag(g.q_fwd[0]));
+        g.q_rc[0].has_flat = g.q_fwd[0].has_flat;
     }
     G.query_len[0] = G.ref_len;
     G.query_loaded[0] = true;

@@ -42,6 +42,13 @@ struct SeqPlanes {
     uint4 *rec_base = nullptr; // filter records {p2 lo, p2 hi, terminator bits, soft bits}, REC_FRONT + words
     uint4 *rec = nullptr;      // = rec_base + REC_FRONT (record 0 = bases 0..31)
     uint32_t term_codes = 0;   // terminator code set the records were built with
+    // zero-run planes (stage B, screen_bound.h: zero_run_codes; built only under a matrix with flat codes): one
+    // allocation = f1 | g1 (1 bit / base: the cell's code is flat / a partner) | F1k | G1k (1 bit / 1024 bases: every
+    // cell of the aligned 1024-base piece exists and is flat / a partner) | flat-cell counter
+    uint32_t *zr = nullptr, *f1 = nullptr, *g1 = nullptr, *F1k = nullptr, *G1k = nullptr;
+    uint32_t coarse_words = 0;
+    uint32_t zero_codes = 0xFFFFFFFFu; // F | G << 8 the planes were built with
+    uint32_t has_flat = 0;     // host copy of the counter
     uint32_t len = 0;
     size_t words = 0; // p2/m1/rec words including back padding
 };
@@ -72,6 +79,9 @@ struct ExtendParams {
     int scores_fit_int8;   // ACGT x ACGT block within [-128,127]: enables the dp4a group path
     int soft_runs;         // lower case or N are NOT terminators under this matrix: walks pass through their runs
     uint32_t win_lo, win_hi; // repeat-masker variant: reference window of the call (0 .. 0xFFFFFFFF otherwise)
+    // zero-run planes of both blocks (zskip != 0: one of the blocks has flat cells, see SeqPlanes)
+    int zskip;
+    const uint32_t *rf1, *rg1, *rF1k, *rG1k, *qf1, *qg1, *qF1k, *qG1k;
 };
 
 struct Anchor { // HSP + the reference iteration it belongs to (dedupe scope)

@@ -240,4 +240,35 @@ static inline uint32_t screen_terminator_codes(const int *sub_mat, int xdrop, ui
     return ~soft & 0xF0u;
 }
 
+// Zero runs (stage B).  Under --ambiguous=n|iupac N scores 0 against everything but a block separator, so a walk that
+// reaches a run of N (an 18 Mb centromere) passes through it cell by cell without its state changing: the running sum
+// stays, the running maximum and its position stay (the maximum moves on strict > only), the X-drop test cannot fire,
+// and the entropy counters are not touched -- every cell of such a tile lies behind the maximum, where the reference
+// counts equal ACGT codes only (into count_del, src/seed_filter.cu:444-451), and two equal ACGT codes never score 0
+// (checked below).  Two code sets make such cells recognisable from bit planes:
+//   F ("flat"):     non-ACGT codes c with sub_mat[c][d] == 0 == sub_mat[d][c] for every d in A/C/G/T;
+//   G ("partners"): codes d with sub_mat[c][d] == 0 == sub_mat[d][c] for every c in F (N itself under --ambiguous).
+// A cell pair (F, G) in either orientation scores 0.  F is empty under the default matrix.
+static inline void zero_run_codes(const int *sub_mat, uint32_t *flat, uint32_t *partners) {
+    uint32_t F = 0, G = 0;
+    bool diag_nonzero = true;
+    for (int d = 0; d < 4; d++)
+        if (sub_mat[d * 9] == 0) diag_nonzero = false;
+    for (int c = 4; c < 8 && diag_nonzero; c++) {
+        bool ok = true;
+        for (int d = 0; d < 4; d++)
+            if (sub_mat[c * 8 + d] != 0 || sub_mat[d * 8 + c] != 0) ok = false;
+        if (ok) F |= 1u << c;
+    }
+    if (F)
+        for (int d = 0; d < 8; d++) {
+            bool ok = true;
+            for (int c = 4; c < 8; c++)
+                if (((F >> c) & 1u) && (sub_mat[c * 8 + d] != 0 || sub_mat[d * 8 + c] != 0)) ok = false;
+            if (ok) G |= 1u << d;
+        }
+    *flat = F;
+    *partners = G;
+}
+
 } // namespace sa

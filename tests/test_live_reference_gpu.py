@@ -78,6 +78,43 @@ def gen_masked_x_ambiguous(rng, n=400_000):
     return ref, q
 
 
+def gen_n_runs(rng, n=600_000, d=0.12):
+    """Runs of N from 33 bases to 70 kb in either sequence, overlapping ones (N opposite N), a run opposite the other
+    sequence's chromosome separator, frequent short soft-masked stretches (HSPs of a few hundred bases: the entropy
+    path).  No indels: both sequences stay on one diagonal, so under --ambiguous=n|iupac the walk crosses a run at 0 per
+    cell and the HSP resumes behind it -- what stage B's zero-run planes skip (kernels_extend.cuh: zero_tile / zero_jump)."""
+    amp = np.frombuffer(b"&", dtype=np.uint8)
+    ref = np.concatenate([genome.random_genome(n // 2, rng), amp, genome.random_genome(n - n // 2 - 1, rng)])
+    q = genome.mutate(ref, d, rng)
+    ref = genome.soft_mask(ref, 0.25, rng, mean_run=80)
+    q = genome.soft_mask(q, 0.25, rng, mean_run=80)
+    # (start, length, flank): clean, closely related flanks on both sides of a run make HSPs cross it -- 400 bases
+    # (score far above 3 x hspthresh: decided by the warp-per-hit kernel) or 45 bases fenced by lower case (hspthresh ..
+    # 3 x hspthresh: the entropy path of the lane-pair kernel; behind a long run the entropy factor rejects the HSP, across
+    # a run of 70 - 150 bases it passes)
+    runs_r = [(20_000, 40, 400), (25_000, 70, 45), (27_000, 150, 45), (40_000, 700, 45), (60_000, 1_100, 400),
+              (90_000, 2_100, 45), (120_000, 5_000, 400), (150_000, 40_000, 45), (n // 2 + 50_000, 70_000, 400),
+              (n - 3_000, 3_000, 45)]
+    runs_q = [(30_000, 33, 400), (33_000, 100, 45), (35_000, 130, 45), (175_000, 10_000, 45), (200_000, 1_500, 400),
+              (215_000, 3_000, 45), (230_000, 36_000, 400), (n // 2 - 9_000, 20_000, 45), (0, 2_500, 400)]
+    for s0, l, w in runs_r + runs_q:
+        for lo, hi in ((max(0, s0 - w), s0), (s0 + l, min(n, s0 + l + w))):
+            if hi <= lo:
+                continue
+            ref[lo:hi] &= 0xDF
+            q[lo:hi] = genome.mutate(ref[lo:hi], 0.04, rng)
+            if w == 45:
+                if lo >= 4: ref[lo - 4:lo] |= 0x20
+                if hi + 4 <= n: ref[hi:hi + 4] |= 0x20
+    keep = ref == ord("&")
+    for s0, l, _ in runs_r:
+        ref[s0:s0 + l] = ord("N")
+    ref[keep] = ord("&")
+    for s0, l, _ in runs_q:
+        q[s0:s0 + l] = ord("N")
+    return ref, q
+
+
 def gen_fresh(rng):
     """Everything at once, small: several chromosomes, soft-masking, N runs, inversions, a repeat family."""
     ref, q = H.gen_masked_multichrom(rng, n=400_000, d=0.22, chroms=3, f_mask=0.2)
@@ -88,7 +125,7 @@ def gen_fresh(rng):
 
 H.GENERATORS.update(ecoli_self=gen_ecoli_self, ecoli_mut40=gen_ecoli_mut40, worm_piece=gen_worm_piece,
                     chr1_like=gen_chr1_like, syn500_piece=gen_syn500_piece, fresh=gen_fresh,
-                    masked_x_ambiguous=gen_masked_x_ambiguous)
+                    masked_x_ambiguous=gen_masked_x_ambiguous, n_runs=gen_n_runs)
 
 # SEGALIGN_LIVE_FULL=1 (tests/golden/check_large.py sets it) runs the self-alignment at E. coli size:
 # the reference kernels need ~270 s for it on a B200 (every main-diagonal hit re-walks the diagonal).
@@ -106,6 +143,13 @@ LIVE_CASES = [
     H.Case("masked_x_ambiguous_n_notransition", "masked_x_ambiguous", ambiguous="n", transition=False, rng_seed=42),
     H.Case("fresh_seed", "fresh", rng_seed=FRESH_SEED, wga_chunk=100_000),
 ]
+
+# long runs of N under --ambiguous: stage B's zero-run skipping, through each of its code paths
+N_RUN_CASES = [
+    H.Case("n_runs_iupac", "n_runs", ambiguous="iupac", rng_seed=51),
+    H.Case("n_runs_n_notransition", "n_runs", ambiguous="n", transition=False, rng_seed=52),
+]
+N_RUN_KNOBS = ["", "SEGALIGN_B200_WIDE=0", "SEGALIGN_B200_ZERO_RUNS=0", "SEGALIGN_B200_FILTER=0", "SEGALIGN_B200_FUSED=0"]
 
 
 def reference_calls(case, workdir):
@@ -162,3 +206,25 @@ def test_backend_matches_live_reference_kernels(case, tmp_path, built):
         got, _ = backend_calls(be, case, ref, query, device_seeding)
         H.assert_calls_equal(got, want, f"{case.name}: backend ({'device seeding' if device_seeding else 'seed vectors'}) "
                                         f"vs the reference's own kernels (seed {case.rng_seed})")
+
+
+@pytest.mark.parametrize("knob", N_RUN_KNOBS, ids=[k or "default" for k in N_RUN_KNOBS])
+@pytest.mark.parametrize("case", N_RUN_CASES, ids=lambda c: c.name)
+def test_n_runs_match_live_reference_kernels(case, knob, tmp_path, built, monkeypatch):
+    """HSPs that cross runs of N (0 per cell under --ambiguous) and hits that walk into such runs: the backend skips
+    the runs (zero-run planes), the reference walks them tile by tile; records must be byte-identical with the skipping on,
+    off, and with every survivor on the lane-pair kernel."""
+    from segalign_b200.backend import Backend
+    if knob:
+        k, v = knob.split("=")
+        monkeypatch.setenv(k, v)
+    ref, query = case.inputs()
+    want, dump = reference_calls(case, tmp_path)
+    assert int(dump.counters[2]) > 100, "the reference found too few HSPs for this to test anything"
+    # the case must contain what it is there for: HSPs longer than the shortest long run, i.e. crossing one
+    assert max(int(w[4][1:]["len"].max()) for w in want if w[4].size > 1) > 5_000
+    for device_seeding in (False, True):
+        be = Backend()
+        be.InitializeInterface(1)
+        got, _ = backend_calls(be, case, ref, query, device_seeding)
+        H.assert_calls_equal(got, want, f"{case.name} [{knob or 'default'}]: backend vs the reference's own kernels")

@@ -113,6 +113,37 @@ def test_rm_backend_matches_cpu_oracle_fresh_inputs(backend, seed):
     H.assert_rm_calls_equal(got, want, "rm backend vs cpu oracle")
 
 
+def gen_rm_n_runs(rng, n=40_000):
+    """A repeat family with runs of N (70 bases to 6 kb) right behind some of its copies and elsewhere: off-diagonal
+    walks cross a run at 0 per cell under --ambiguous=iupac (N opposite a base of another copy), on the main diagonal N
+    meets N.  What stage B's zero-run planes must skip without changing a record."""
+    seq, _ = H.gen_repeats(rng, n=n, copies=40, elem=400, elem_div=0.06, low_complexity=6)
+    for s0, l in [(3_000, 70), (7_000, 150), (12_000, 1_100), (20_000, 6_000), (31_000, 2_500), (n - 1_500, 1_500)]:
+        seq[s0:s0 + l] = ord("N")
+    return seq, seq.copy()
+
+
+H.GENERATORS.update(rm_n_runs=gen_rm_n_runs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("knob", ["", "SEGALIGN_B200_WIDE=0", "SEGALIGN_B200_ZERO_RUNS=0"], ids=["default", "lane_pair", "no_skip"])
+def test_rm_backend_matches_cpu_oracle_across_n_runs(built, knob, monkeypatch):
+    from segalign_b200.backend import Backend
+    if knob:
+        k, v = knob.split("=")
+        monkeypatch.setenv(k, v)
+    case = H.Case("rm_n_runs", "rm_n_runs", rng_seed=77, ambiguous="iupac", lastz_interval=9_000, wga_chunk=4_000)
+    seq, _ = case.inputs()
+    want = H.run_rm_cpu_oracle(case, 0.6, seq, max_hits_device=748058112)
+    assert sum(w[6].size - 1 for w in want) > 200
+    for device_seeding in (False, True):
+        be = Backend()
+        be.InitializeInterface(1)
+        got = H.run_rm_backend(be, case, 0.6, seq, device_seeding=device_seeding)
+        H.assert_rm_calls_equal(got, want, f"rm backend [{knob or 'default'}] vs cpu oracle across runs of N")
+
+
 @needs_golden
 @pytest.mark.gpu
 @pytest.mark.skipif(not H.RM_NEW_RUNNER.exists(), reason="oracle/_ref/rm_new_runner not built (needs /root/reference at build time)")
