@@ -64,46 +64,6 @@ __device__ __forceinline__ void count_fast_tile(uint64_t rw, uint64_t qw, int nl
     }
 }
 
-// ---- zero runs (screen_bound.h: zero_run_codes; planes: sa_common.cuh SeqPlanes) ------------------------------
-// All 32 cell pairs of a tile (reference cells rc0.., query cells qc0..) are (flat, partner) pairs in one orientation
-// or the other: 32 scores of 0, none of them between equal ACGT codes.  A walk leaves such a tile as it entered it --
-// same running sum, same maximum at the same position (the maximum moves on strict > only), no X-drop, and no entropy
-// counter touched: the tile lies behind the maximum, where :444-451 counts equal ACGT codes only.
-__device__ __forceinline__ bool zero_tile(const ExtendParams &P, uint32_t rc0, uint32_t qc0) {
-    const uint32_t fr = load_m1_window(P.rf1, rc0), fq = load_m1_window(P.qf1, qc0);
-    if ((fr | fq) != 0xFFFFFFFFu) return false; // the common case: two window loads
-    const uint32_t gr = load_m1_window(P.rg1, rc0), gq = load_m1_window(P.qg1, qc0);
-    return ((fr & gq) | (fq & gr)) == 0xFFFFFFFFu;
-}
-// Cells from position c upwards (c, c+1, ..) / from top-1 downwards that lie in 1024-base pieces marked in the
-// coarse plane k1 (at most 32 pieces = 32 768 cells per call).
-__device__ __forceinline__ uint32_t coarse_span_up(const uint32_t *__restrict__ k1, uint32_t c) {
-    const uint32_t w = load_m1_window(k1, c >> 10); // pieces c >> 10 .. + 31
-    const uint32_t n = w == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~w) - 1u;
-    return n ? n * 1024u - (c & 1023u) : 0u;
-}
-__device__ __forceinline__ uint32_t coarse_span_down(const uint32_t *__restrict__ k1, uint32_t top) {
-    if (top == 0) return 0u;
-    const uint32_t b = (top - 1u) >> 10; // piece of the first cell to visit: bit 31 of w
-    const uint32_t w = b >= 31u ? load_m1_window(k1, b - 31u) : __ldg(k1) << (31u - b);
-    const uint32_t n = (uint32_t)__clz((int)~w); // leading ones (32 for all-ones)
-    return n ? (n - 1u) * 1024u + ((top - 1u) & 1023u) + 1u : 0u;
-}
-// Cells (a multiple of 32) a walk may skip: right -- the next cells are r, r+1, .. / q, q+1, ..; left -- the next
-// cells are r-1, r-2, .. / q-1, q-2, ...  All of them lie in pieces that are entirely flat on one block and entirely
-// partners on the other, hence inside both blocks.
-__device__ __forceinline__ uint32_t zero_jump(const ExtendParams &P, uint32_t r, uint32_t q, bool left) {
-    uint32_t k;
-    if (!left) {
-        k = min(coarse_span_up(P.rF1k, r), coarse_span_up(P.qG1k, q));
-        if (k < 32u) k = min(coarse_span_up(P.qF1k, q), coarse_span_up(P.rG1k, r));
-    } else {
-        k = min(coarse_span_down(P.rF1k, r), coarse_span_down(P.qG1k, q));
-        if (k < 32u) k = min(coarse_span_down(P.qF1k, q), coarse_span_down(P.rG1k, r));
-    }
-    return k & ~31u;
-}
-
 // One direction of one hit (:300-453 right, :457-604 left), exact.
 //   right: cells k = 0,1,..  at (r0+k, q0+k); best starts at (0,-1)
 //   left : cells k = 1,2,..  at (r0-k, q0-k); best starts at (0, 0)
@@ -200,10 +160,10 @@ __device__ __forceinline__ DirResult extend_dir(const ExtendParams &P, const int
                 for (int c = 0; c < 4; c++) { C.cnt[c] += C.del[c]; C.del[c] = 0; }
             }
             count_fast_tile(rw, qw, mp - base + 1, C);
-        } else if (P.zskip && inside && zero_tile(P, rc0, qc0)) {
+        } else if (P.zskip && inside && zero_tile(P.rz, P.qz, rc0, qc0)) {
             // a tile of zero-scoring pairs without an ACGT match changes nothing; neither do the pieces behind it that
-            // are flat on one block and partners on the other (an N run of megabases: 32 768 cells per trip)
-            const uint32_t k = max(32u, zero_jump(P, left ? r0 - t : rc0, left ? q0 - t : qc0, left));
+            // are flat on one block and partners on the other (an N run of megabases: 32 768 cells per trip); zero_runs.h
+            const uint32_t k = max(32u, zero_jump(P.rz, P.qz, left ? r0 - t : rc0, left ? q0 - t : qc0, left));
             t += k;
             *cells += k;
             continue;

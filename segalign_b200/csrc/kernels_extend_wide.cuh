@@ -127,9 +127,9 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
     uint32_t t = 0; // cells of this direction already walked
     for (;;) {
         if (P.zskip && (!left || (r0 >= t && q0 >= t))) {
-            // the next cells lie in 1024-base pieces that are flat on one block and partners on the other (kernels_extend.cuh:
-            // zero runs): nothing changes over them.  Warp-uniform.
-            const uint32_t k = zero_jump(P, left ? r0 - t : r0 + t, left ? q0 - t : q0 + t, left);
+            // the next cells lie in 1024-base pieces that are flat on one block and partners on the other (zero_runs.h):
+            // nothing changes over them.  Warp-uniform.
+            const uint32_t k = zero_jump(P.rz, P.qz, left ? r0 - t : r0 + t, left ? q0 - t : q0 + t, left);
             if (k >= 1024u) { t += k; continue; }
         }
         // ---- every lane summarises tile `lane` of the next 32
@@ -148,7 +148,7 @@ __device__ __forceinline__ DirResult wide_extend_dir(const ExtendParams &P, cons
         const bool clean = m == 0;
         // tiles that touch a block end always go to the cell-by-cell code (:420 rule); tiles with non-ACGT
         // cells do so unless such cells can be walked through (N / lower case not being terminators)
-        const bool zero = P.zskip && inside && !clean && zero_tile(P, rc0, qc0); // 32 scores of 0: the empty summary
+        const bool zero = P.zskip && inside && !clean && zero_tile(P.rz, P.qz, rc0, qc0); // 32 scores of 0: the empty summary
         const bool summarised = clean || zero || (inside && P.soft_runs);
         int sum = 0, maxpre = zero ? 0 : -(1 << 29), argpos = 0, minpre = 0, dropub = 0;
         if (zero) {

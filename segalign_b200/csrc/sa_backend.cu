@@ -530,8 +530,8 @@ int run_pipeline(Workspace *w, const CallInput &in, int rev, uint32_t buffer, sa
     P.soft_runs = (((G.strict_term_codes >> L_NT) & 1u) == 0 || ((G.strict_term_codes >> N_NT) & 1u) == 0) ? 1 : 0;
     P.win_lo = in.win_lo; P.win_hi = in.win_hi;
     P.zskip = (g.ref.zr && q.zr && (g.ref.has_flat || q.has_flat)) ? 1 : 0;
-    P.rf1 = g.ref.f1; P.rg1 = g.ref.g1; P.rF1k = g.ref.F1k; P.rG1k = g.ref.G1k;
-    P.qf1 = q.f1; P.qg1 = q.g1; P.qF1k = q.F1k; P.qG1k = q.G1k;
+    P.rz = ZeroPlanes{g.ref.f1, g.ref.g1, g.ref.F1k, g.ref.G1k};
+    P.qz = ZeroPlanes{q.f1, q.g1, q.F1k, q.G1k};
     FilterParams F;
     F.rrec = g.ref.rec; F.qrec = q.rec;
     F.rp2 = g.ref.p2; F.rsoft = g.ref.softmap; F.ref_has_soft = g.ref.has_soft ? 1 : 0;

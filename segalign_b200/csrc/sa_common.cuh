@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/segalign_b200.h"
+#include "zero_runs.h"
 
 namespace sa {
 
@@ -79,9 +80,9 @@ struct ExtendParams {
     int scores_fit_int8;   // ACGT x ACGT block within [-128,127]: enables the dp4a group path
     int soft_runs;         // lower case or N are NOT terminators under this matrix: walks pass through their runs
     uint32_t win_lo, win_hi; // repeat-masker variant: reference window of the call (0 .. 0xFFFFFFFF otherwise)
-    // zero-run planes of both blocks (zskip != 0: one of the blocks has flat cells, see SeqPlanes)
+    // zero-run planes of both blocks (zskip != 0: one of the blocks has flat cells, see SeqPlanes and zero_runs.h)
     int zskip;
-    const uint32_t *rf1, *rg1, *rF1k, *rG1k, *qf1, *qg1, *qF1k, *qG1k;
+    ZeroPlanes rz, qz;
 };
 
 struct Anchor { // HSP + the reference iteration it belongs to (dedupe scope)
