@@ -82,7 +82,7 @@ def gen_n_runs(rng, n=600_000, d=0.12):
     """Runs of N from 33 bases to 70 kb in either sequence, overlapping ones (N opposite N), a run opposite the other
     sequence's chromosome separator, frequent short soft-masked stretches (HSPs of a few hundred bases: the entropy
     path).  No indels: both sequences stay on one diagonal, so under --ambiguous=n|iupac the walk crosses a run at 0 per
-    cell and the HSP resumes behind it -- what stage B's zero-run planes skip (kernels_extend.cuh: zero_tile / zero_jump)."""
+    cell and the HSP resumes behind it -- what stage B's zero-run planes skip (zero_runs.h: zero_tile / zero_jump)."""
     amp = np.frombuffer(b"&", dtype=np.uint8)
     ref = np.concatenate([genome.random_genome(n // 2, rng), amp, genome.random_genome(n - n // 2 - 1, rng)])
     q = genome.mutate(ref, d, rng)
