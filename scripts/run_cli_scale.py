@@ -29,6 +29,19 @@ def fasta(path, chroms, prefix):
             f.write(b"\n")
 
 
+def digest(folder: Path) -> str:
+    """sha256 over (name, bytes) of every file of the output folder, in name order."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(folder.glob("*")):
+        h.update(f.name.encode())
+        data = f.read_bytes()
+        if f.name == "lastz_commands.txt":   # one line per finished interval, in completion order (as the reference's printer)
+            data = b"\n".join(sorted(data.split(b"\n")))
+        h.update(data)
+    return h.hexdigest()
+
+
 def main():
     rng = np.random.default_rng(20261017)
     # reference: 6 records of 52 Mb -> blocks close behind the record that passes 100 Mb: 3 blocks of 104 Mb
@@ -40,9 +53,22 @@ def main():
     fasta(work / "query.fa", qry, "chrQ")
     out = work / "out"
     out.mkdir()
+    extra_args = [a for a in sys.argv[1:] if a.startswith("--num_gpu")]
+    one_gpu_digest = None
+    if "--compare-one-gpu" in sys.argv[1:]:
+        # the same input on ONE GPU first: every output file must come out byte-identical on the whole pool
+        p1 = subprocess.run([str(CLI), str(work / "ref.fa"), str(work / "query.fa"), "/data", f"--out_dir={out}",
+                             "--seq_block_size=100000000", "--nogapped", "--num_gpu=1"], capture_output=True, text=True)
+        if p1.returncode != 0:
+            print(json.dumps({"error": p1.stderr[-500:], "rc": p1.returncode, "run": "one gpu"}))
+            return 1
+        one_gpu_line = [l for l in p1.stderr.splitlines() if l.startswith("ref blocks")][-1]
+        one_gpu_digest = digest(out)
+        for f in out.glob("*"):
+            f.unlink()
     t0 = time.perf_counter()
     p = subprocess.run([str(CLI), str(work / "ref.fa"), str(work / "query.fa"), "/data", f"--out_dir={out}",
-                        "--seq_block_size=100000000", "--nogapped"], capture_output=True, text=True)
+                        "--seq_block_size=100000000", "--nogapped", *extra_args], capture_output=True, text=True)
     wall = time.perf_counter() - t0
     if p.returncode != 0:
         print(json.dumps({"error": p.stderr[-500:], "rc": p.returncode}))
@@ -59,6 +85,14 @@ def main():
            "ms_ref_upload_encode_total": nums[9], "ms_seed_pos_tables_total": nums[10], "ms_query_upload_encode_total": nums[11],
            "gbp_query_x_ref_blocks_per_s": round(qbases * nums[0] / nums[8] / 1e9, 4),
            "segments_bytes": sum(f.stat().st_size for f in segs)}
+    gl = [l for l in p.stderr.splitlines() if "GPU" in l]
+    if gl:
+        res["gpu_line"] = gl[0][:200]
+    if one_gpu_digest is not None:
+        res["one_gpu"] = {"summary_line": one_gpu_line, "output_files_identical_to_pool_run": digest(out) == one_gpu_digest}
+        if not res["one_gpu"]["output_files_identical_to_pool_run"]:
+            print(json.dumps(res))
+            return 2
     print(json.dumps(res))
     for f in list(out.glob("*")) + list(work.glob("*.fa")):
         f.unlink()
