@@ -191,6 +191,9 @@ typedef struct sa_pipeline_report {
     double seconds;
     /* wall milliseconds summed over the run's block-level calls (all GPUs of the pool work concurrently) */
     double ms_ref_upload, ms_table_build, ms_query_upload;
+    /* parts of `seconds`: reading + blocking the two FASTA inputs; device discovery + processor set-up; everything from the
+     * first reference block's upload to the last segment file (the part the metric of bench.py corresponds to) */
+    double seconds_read_input, seconds_device_init, seconds_align;
 } sa_pipeline_report;
 int sa_pipeline_run(const sa_pipeline_config *cfg, sa_pipeline_report *report);
 /* The host-only part of sa_pipeline_run: inputs -> blocks -> intervals, block name files, and

@@ -83,7 +83,9 @@ def main():
            "ref_blocks": int(nums[0]), "query_blocks": int(nums[1]), "intervals": int(nums[2]), "calls": int(nums[3]),
            "hits": int(nums[5]), "hsps": int(nums[6]), "segment_files": len(segs), "driver_seconds": nums[8],
            "ms_ref_upload_encode_total": nums[9], "ms_seed_pos_tables_total": nums[10], "ms_query_upload_encode_total": nums[11],
+           "seconds_read_input": nums[12], "seconds_device_init": nums[13], "seconds_align": nums[14],
            "gbp_query_x_ref_blocks_per_s": round(qbases * nums[0] / nums[8] / 1e9, 4),
+           "gbp_query_x_ref_blocks_per_s_alignment_only": round(qbases * nums[0] / max(1e-9, nums[14]) / 1e9, 4),
            "segments_bytes": sum(f.stat().st_size for f in segs)}
     gl = [l for l in p.stderr.splitlines() if "GPU" in l]
     if gl:

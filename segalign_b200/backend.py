@@ -55,7 +55,8 @@ class SaPipelineConfig(C.Structure):
 class SaPipelineReport(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("ref_blocks", "query_blocks", "intervals", "calls", "seeds", "hits",
                                           "hsps", "segment_files")] + \
-               [(n, C.c_double) for n in ("seconds", "ms_ref_upload", "ms_table_build", "ms_query_upload")]
+               [(n, C.c_double) for n in ("seconds", "ms_ref_upload", "ms_table_build", "ms_query_upload",
+                                          "seconds_read_input", "seconds_device_init", "seconds_align")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -83,11 +83,11 @@ int main(int argc, char **argv) {
     }
     fprintf(stderr, "ref blocks %llu, query blocks %llu, intervals %llu, SeedAndFilter calls %llu, seeds %llu, hits %llu, "
                     "HSPs %llu, segment files %llu, %.2f s (reference blocks: upload + encode %.1f ms, seed position tables %.1f ms; "
-                    "query blocks: upload + encode %.1f ms)\n",
+                    "query blocks: upload + encode %.1f ms); reading the inputs %.2f s, device set-up %.2f s, alignment %.2f s\n",
             (unsigned long long)rep.ref_blocks, (unsigned long long)rep.query_blocks, (unsigned long long)rep.intervals,
             (unsigned long long)rep.calls, (unsigned long long)rep.seeds, (unsigned long long)rep.hits,
             (unsigned long long)rep.hsps, (unsigned long long)rep.segment_files, rep.seconds, rep.ms_ref_upload,
-            rep.ms_table_build, rep.ms_query_upload);
+            rep.ms_table_build, rep.ms_query_upload, rep.seconds_read_input, rep.seconds_device_init, rep.seconds_align);
     (void)debug; (void)markend;
     return 0;
 }
