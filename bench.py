@@ -527,7 +527,10 @@ def run_ours(args):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        be.ShutdownProcessor()   # LASTZ wants the host cores; nothing of ours runs beside it
+        try:
+            be.ShutdownProcessor()   # LASTZ wants the host cores; nothing of ours runs beside it
+        except Exception:  # noqa: BLE001 -- already down (a secondary workload gave up half-way)
+            pass
         cpu_baseline = lastz_baseline(wl, budget_s=args.cpu_budget)
 
     if rank == 0:
@@ -750,20 +753,28 @@ def extra_workloads(be, args, pool, nthreads):
         # 248 Mb record, half of it soft-masked, an 18 Mb and forty 50 kb runs of N, IUPAC letters at 1e-5; the query
         # is a 100 Mb slice of its 40 %-diverged copy with its own masking and N runs.  Other scoring options than
         # the main legs: the processor is set up again (the last thing this function does).
-        ref, q = make_chr1_pair()
-        be.ShutdownProcessor()
-        be.InitializeInterface(1, first_device=int(os.environ.get("LOCAL_RANK", "0")))
-        be.GenerateShapePos(SEED_SHAPE)
-        be.InitializeProcessor(False, genome.DEFAULT_WGA_CHUNK, span, iupac_matrix(), XDROP, HSPTHRESH, False)
-        run("configs3_chr1_scale_notransition_iupac", ref, q, 3,
-            "BASELINE configs[3] flags at chr1 scale, synthetic: 248 Mb reference record (50 % soft-masked, 18 Mb + 40 x 50 kb "
-            "of N, IUPAC letters) x 100 Mb query slice (40 % diverged), --notransition --ambiguous=iupac; 1 GPU",
-            transition=False)
-        if not args.no_reference_gpu:
-            r = reference_gpu_compare(be, ref, q, span, args, False, iupac_matrix(), args.reference_gpu_mb)
-            out["configs3_chr1_scale_notransition_iupac"]["reference_gpu"] = {
-                k: r[k] for k in ("seconds", "ours_seconds", "speedup", "identical", "calls", "hits", "hsps",
-                                  "query_slice_bp", "unavailable") if k in r}
+        # A secondary workload must not cost the headline line: anything but a parity failure (AssertionError:
+        # records differ from the reference kernels') is reported in place of the number.
+        name = "configs3_chr1_scale_notransition_iupac"
+        try:
+            ref, q = make_chr1_pair()
+            be.ShutdownProcessor()
+            be.InitializeInterface(1, first_device=int(os.environ.get("LOCAL_RANK", "0")))
+            be.GenerateShapePos(SEED_SHAPE)
+            be.InitializeProcessor(False, genome.DEFAULT_WGA_CHUNK, span, iupac_matrix(), XDROP, HSPTHRESH, False)
+            run(name, ref, q, 3,
+                "BASELINE configs[3] flags at chr1 scale, synthetic: 248 Mb reference record (50 % soft-masked, 18 Mb + 40 x 50 kb "
+                "of N, IUPAC letters) x 100 Mb query slice (40 % diverged), --notransition --ambiguous=iupac; 1 GPU",
+                transition=False)
+            if not args.no_reference_gpu:
+                r = reference_gpu_compare(be, ref, q, span, args, False, iupac_matrix(), args.reference_gpu_mb)
+                out[name]["reference_gpu"] = {
+                    k: r[k] for k in ("seconds", "ours_seconds", "speedup", "identical", "calls", "hits", "hsps",
+                                      "query_slice_bp", "unavailable") if k in r}
+        except AssertionError:
+            raise
+        except Exception as e:  # noqa: BLE001 -- host memory, a missing runner, a time-out
+            out.setdefault(name, {})["error"] = "%s: %s" % (type(e).__name__, str(e)[:300])
     return out
 
 
