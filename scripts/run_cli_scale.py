@@ -44,10 +44,20 @@ def digest(folder: Path) -> str:
 
 def main():
     rng = np.random.default_rng(20261017)
-    # reference: 6 records of 52 Mb -> blocks close behind the record that passes 100 Mb: 3 blocks of 104 Mb
-    ref = [genome.soft_mask(genome.random_genome(52_000_000, rng), 0.3, rng) for _ in range(6)]
-    # query: 30 %-diverged copies of 4 of them + their own masking -> 2 blocks of 104 Mb
-    qry = [genome.soft_mask(genome.mutate(np.where(c >= 97, c - 32, c).astype(np.uint8), 0.30, rng), 0.3, rng) for c in ref[:4]]
+    chr1 = "--chr1" in sys.argv[1:]
+    if chr1:
+        # BASELINE configs[3] at its block size through the C++ driver: bench.py's secondary workload of that name
+        # (one 248 Mb record x a 100 Mb query record, --notransition --ambiguous=iupac), one block each
+        import bench
+        r, q = bench.make_chr1_pair()
+        ref, qry = [r], [q]
+        flags, block = ["--notransition", "--ambiguous=iupac"], 500_000_000
+    else:
+        # reference: 6 records of 52 Mb -> blocks close behind the record that passes 100 Mb: 3 blocks of 104 Mb
+        ref = [genome.soft_mask(genome.random_genome(52_000_000, rng), 0.3, rng) for _ in range(6)]
+        # query: 30 %-diverged copies of 4 of them + their own masking -> 2 blocks of 104 Mb
+        qry = [genome.soft_mask(genome.mutate(np.where(c >= 97, c - 32, c).astype(np.uint8), 0.30, rng), 0.3, rng) for c in ref[:4]]
+        flags, block = [], 100_000_000
     work = Path(tempfile.mkdtemp(prefix="sa_cli_"))
     fasta(work / "ref.fa", ref, "chrR")
     fasta(work / "query.fa", qry, "chrQ")
@@ -58,7 +68,7 @@ def main():
     if "--compare-one-gpu" in sys.argv[1:]:
         # the same input on ONE GPU first: every output file must come out byte-identical on the whole pool
         p1 = subprocess.run([str(CLI), str(work / "ref.fa"), str(work / "query.fa"), "/data", f"--out_dir={out}",
-                             "--seq_block_size=100000000", "--nogapped", "--num_gpu=1"], capture_output=True, text=True)
+                             f"--seq_block_size={block}", "--nogapped", "--num_gpu=1", *flags], capture_output=True, text=True)
         if p1.returncode != 0:
             print(json.dumps({"error": p1.stderr[-500:], "rc": p1.returncode, "run": "one gpu"}))
             return 1
@@ -68,7 +78,7 @@ def main():
             f.unlink()
     t0 = time.perf_counter()
     p = subprocess.run([str(CLI), str(work / "ref.fa"), str(work / "query.fa"), "/data", f"--out_dir={out}",
-                        "--seq_block_size=100000000", "--nogapped", *extra_args], capture_output=True, text=True)
+                        f"--seq_block_size={block}", "--nogapped", *flags, *extra_args], capture_output=True, text=True)
     wall = time.perf_counter() - t0
     if p.returncode != 0:
         print(json.dumps({"error": p.stderr[-500:], "rc": p.returncode}))
@@ -78,7 +88,7 @@ def main():
     segs = list(out.glob("*.segments"))
     qbases = sum(c.size for c in qry)
     res = {"what": "segalign_b200_cli (sa_pipeline_run): FASTA -> blocks -> every reference block x every query block -> tmp*.segments",
-           "ref_bp": int(sum(c.size for c in ref)), "query_bp": int(qbases), "seq_block_size": 100_000_000,
+           "ref_bp": int(sum(c.size for c in ref)), "query_bp": int(qbases), "seq_block_size": block, "flags": flags,
            "summary_line": line, "wall_s_incl_fasta_read": round(wall, 2),
            "ref_blocks": int(nums[0]), "query_blocks": int(nums[1]), "intervals": int(nums[2]), "calls": int(nums[3]),
            "hits": int(nums[5]), "hsps": int(nums[6]), "segment_files": len(segs), "driver_seconds": nums[8],
